@@ -1,0 +1,186 @@
+/*
+ * b200_spectral.h -- C ABI of libb200spectral.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the spectral-radius hot path of ars2240/optWBoundEigenval.
+ * The reference has no FFI: the seam is the Python class `HVPOperator`
+ * (opt.py:48-192) and the methods `comp_rho` / `comp_gradrho` of
+ * `OptWBoundEignVal` (opt.py:418-542).  Every entry point below names the
+ * reference lines whose work it replaces.  The Python side
+ * (optwboundeigenval_b200/hvp_operator.py) binds these with ctypes and passes
+ * raw device pointers obtained from `tensor.data_ptr()`; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative code on failure; the
+ *    message is available from b2s_last_error() (thread local);
+ *  - all pointers named d_* are DEVICE pointers borrowed for the call, h_* are
+ *    HOST pointers; the library owns only its plan and workspaces;
+ *  - work is enqueued on the plan's stream (set with b2s_plan_set_stream, the
+ *    default is the legacy default stream); only functions documented as
+ *    synchronising wait for the device;
+ *  - a plan is not re-entrant: one thread per plan at a time;
+ *  - flat parameter vectors follow `model.parameters()` order, shared
+ *    parameters once (opt.py:102,135,146,191).
+ */
+#ifndef B200_SPECTRAL_H
+#define B200_SPECTRAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_ABI_VERSION 1
+
+/* ---- tape description ------------------------------------------------------------ */
+
+/* One activation tensor, NCHW inside a (possibly larger) per-sample buffer; a
+ * channel-concatenation is expressed by views with different `offset` into the
+ * same buffer (densenet.py:21,42 `torch.cat`). Linear activations use H=W=1. */
+typedef struct {
+    int32_t buf;            /* buffer id, 0 is the network input */
+    int32_t C, H, W;
+    int64_t offset;         /* element offset of this view inside one sample of the buffer */
+    int64_t sample_stride;  /* elements between consecutive samples of the buffer */
+} b2s_tensor;
+
+enum {
+    B2S_OP_CONV = 1,     /* nn.Conv2d and nn.Linear (H=W=1, 1x1 kernel) */
+    B2S_OP_BN = 2,       /* train-mode nn.BatchNorm2d / BatchNorm1d */
+    B2S_OP_RELU = 3,     /* standalone ReLU (normally fused into its producer) */
+    B2S_OP_MAXPOOL = 4,
+    B2S_OP_AVGPOOL = 5,  /* kernel == stride, no padding; adaptive (1,1) maps to kernel = H */
+    B2S_OP_COPY = 6      /* physical copy of a view (fallback for concatenations that cannot alias) */
+};
+
+enum {
+    B2S_F_RELU = 1,      /* a ReLU is fused behind this op */
+    B2S_F_FIRST = 2,     /* input is network data: no input tangent, no input adjoint */
+    B2S_F_BWD_ACC = 4    /* backward accumulates into the input adjoint instead of overwriting it */
+};
+
+typedef struct {
+    int32_t kind;
+    int32_t flags;
+    int32_t in;             /* tensor id */
+    int32_t out;            /* tensor id */
+    int64_t w_off;          /* weight (Conv/Linear) or gamma (BN) offset in the flat parameter vector, -1 if none */
+    int64_t b_off;          /* bias / beta offset, -1 if none */
+    int32_t kh, kw, sh, sw, ph, pw;
+    int32_t slot;           /* BN: index into the running-statistics pointer tables; MAXPOOL: argmax slot */
+    float eps;              /* BN epsilon */
+    float momentum;         /* BN momentum (<0: cumulative average, nn.BatchNorm2d(momentum=None)) */
+} b2s_op;
+
+/* loss heads */
+enum {
+    B2S_HEAD_CE = 1,            /* logits -> CrossEntropyLoss(mean)                       densenet.py:121 */
+    B2S_HEAD_SOFTMAX_CE = 2,    /* logits -> softmax -> CrossEntropyLoss(mean)            forest_data.py:88, usps_data.py:335 */
+    B2S_HEAD_WBCE = 3,          /* logits -> W_BCEWithLogitsLoss                          dcnn.py:375-400 */
+    B2S_HEAD_SIGMOID_WBCE = 4   /* logits -> sigmoid -> W_BCEWithLogitsLoss               dcnn.py:275,375-400 */
+};
+
+typedef struct b2s_plan b2s_plan;
+
+/* ---- library ----------------------------------------------------------------------- */
+int b2s_abi_version(void);
+const char* b2s_last_error(void);
+/* number of kernels this library has launched (or captured graph kernel nodes replayed) since load */
+int64_t b2s_launch_count(void);
+
+/* ---- plan -------------------------------------------------------------------------- */
+/* Compiles a tape into an execution plan and allocates its workspaces (value, tangent
+ * and adjoint caches for `max_batch` samples).  buf_elems[b] = elements per sample of
+ * buffer b.  logits = tensor id feeding the loss head. Replaces the autograd graph that
+ * HVPOperator.prepare_grad builds with create_graph=True (opt.py:175-192). */
+int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors,
+                    const int64_t* buf_elems, int32_t n_bufs,
+                    const b2s_op* ops, int32_t n_ops,
+                    int32_t logits, int32_t head, int64_t n_params,
+                    int32_t max_batch, int32_t device, b2s_plan** out);
+int b2s_plan_destroy(b2s_plan* p);
+int b2s_plan_set_stream(b2s_plan* p, void* cuda_stream);
+/* use_graphs != 0: each pass is captured once per batch size into a CUDA graph and replayed */
+int b2s_plan_set_graphs(b2s_plan* p, int32_t use_graphs);
+int64_t b2s_plan_workspace_bytes(const b2s_plan* p);
+/* device pointers (float*) of the running_mean / running_var tensors of BN slot `slot`
+ * (updated in place by the base pass exactly like a train-mode forward, opt.py:181,421) */
+int b2s_plan_set_bn_buffers(b2s_plan* p, int32_t slot, void* d_running_mean, void* d_running_var);
+
+/* ---- the three passes ---------------------------------------------------------------- */
+/* Base pass = HVPOperator.prepare_grad (opt.py:175-192): forward, loss, gradient.
+ * d_params: fp32 [n_params]; d_x: fp32 [batch, ...]; d_y: int64 [batch] class labels
+ * (CE heads) or fp32 [batch, C] targets with d_coef fp32 [batch, C] per-entry weights
+ * already divided by the valid counts (WBCE heads; d_coef NULL for CE).
+ * loss_scale multiplies the loss (1/global_batch for mean-reduced CE).
+ * d_grad_out: fp64 [n_params] or NULL.  Asynchronous. */
+int b2s_base_pass(b2s_plan* p, const float* d_params, const float* d_x, const void* d_y,
+                  const float* d_coef, int32_t batch, double loss_scale,
+                  double* d_grad_out, double* d_loss_out);
+/* H*v = HVPOperator.Hv(vec, storedGrad=True) (opt.py:77-108). d_v fp64 [n_params]
+ * (rounded to fp32 as the reference's cast does), d_out fp64 [n_params]. Asynchronous. */
+int b2s_hv(b2s_plan* p, const double* d_v, double* d_out);
+/* grad_w (v^T H v) = HVPOperator.vGHv (opt.py:110-152). Asynchronous. */
+int b2s_vghv(b2s_plan* p, const double* d_v, double* d_out);
+/* fp32 results of the last passes, device pointers owned by the plan (float [n_params]) */
+const float* b2s_grad_f32(const b2s_plan* p);
+const float* b2s_hv_f32(const b2s_plan* p);
+
+/* ---- spectral-radius iteration ------------------------------------------------------- */
+typedef struct {
+    int32_t max_iter;        /* min(ndim, max_pow_iter)                                     opt.py:447 */
+    double eps;              /* pow_iter_eps                                                opt.py:480 */
+    const double* h_alpha;   /* host array [max_iter] of relaxation factors, NULL = all 1   opt.py:489 */
+    int32_t precond;         /* 1: v_new = v + alpha * T(r) with the K-FAC map installed    opt.py:491-493 */
+} b2s_power_cfg;
+
+typedef struct {
+    int32_t iters;           /* index i of the last iteration, as comp_rho returns it       opt.py:533 */
+    int32_t converged;       /* 0 when all three stopping values stayed above eps           opt.py:513 */
+    double lam, norm, rn, vnn;
+    double stop[3];
+} b2s_power_result;
+
+/* comp_rho's loop (opt.py:447-498) on the device: HVP + fused vector kernels per
+ * iteration, 4 scalars read back per iteration for the stopping test.  d_v fp64
+ * [n_params] in/out: start vector on entry, on exit the vector self.v would hold
+ * (opt.py:508).  h_traj: NULL or host array [max_iter*5] receiving the rows
+ * (i, lam, n, rn, vnn) of the verbose log (opt.py:466).  Synchronises. */
+int b2s_power_iterate(b2s_plan* p, double* d_v, const b2s_power_cfg* cfg,
+                      b2s_power_result* h_result, double* h_traj);
+
+/* ---- the vector part of the iteration on its own -----------------------------------------
+ * A b2s_pistate holds the fp64 eigenvector / residual double buffers and every scalar of the
+ * loop on the device.  b2s_power_iterate drives one internally; it is exposed so the two fused
+ * vector kernels can be measured against the HBM roofline at any length n and parity-tested
+ * against opt.py:455-498 without a network. */
+typedef struct b2s_pistate b2s_pistate;
+int b2s_pi_create(int64_t n, int32_t max_iter_capacity, int32_t device, b2s_pistate** out);
+int b2s_pi_destroy(b2s_pistate* s);
+/* start a run: copies d_v0 (fp64 [n]) in, rounds it to fp32, clears lam_old / r_old (opt.py:436) */
+int b2s_pi_reset(b2s_pistate* s, const double* d_v0, const b2s_power_cfg* cfg, void* stream);
+/* fp32 rounding of the current vector: the input of the next HVP (device pointer, fixed for the
+ * lifetime of the state) */
+const float* b2s_pi_v32(const b2s_pistate* s);
+/* vector work of one iteration given d_hv = H*v (fp32 [n]): pass A + pass B. Asynchronous. */
+int b2s_pi_step(b2s_pistate* s, const float* d_hv, void* stream);
+/* preconditioned variant only (cfg.precond = 1): after b2s_pi_step, d_r = b2s_pi_residual() holds
+ * r; the caller maps it through T and finishes the update v <- normalise(v + alpha*Tr). */
+const double* b2s_pi_residual(b2s_pistate* s, void* stream);   /* synchronises */
+int b2s_pi_precond_update(b2s_pistate* s, const double* d_Tr, void* stream);
+/* 1 once a stopping test fired or the iterations ran out (synchronises `stream`) */
+int b2s_pi_done(b2s_pistate* s, void* stream);
+/* reads the scalars back (synchronises `stream`); d_v_out (fp64 [n]) receives the vector self.v
+ * would hold, may be NULL; h_traj [iters+1][5] may be NULL */
+int b2s_pi_result(b2s_pistate* s, b2s_power_result* h_result, double* h_traj, double* d_v_out,
+                  void* stream);
+
+/* ---- data parallelism (one process per GPU) ------------------------------------------- */
+int b2s_comm_unique_id(void* h_id128);                       /* 128 bytes, rank 0 */
+int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world);
+int b2s_comm_destroy(b2s_plan* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SPECTRAL_H */

@@ -1,0 +1,272 @@
+// bn.cu -- train-mode BatchNorm jets (value, tangent, second-order; forward and adjoint).
+//
+// The reference differentiates native_batch_norm twice / three times through autograd
+// (opt.py:99,132,143 with model.train() forced at opt.py:421).  Here the layer is written as
+//     mu = mean(x), c = x - mu, s = mean(c*c), r = (s+eps)^(-1/2), xh = c*r, y = gamma*xh + beta
+//     xbar = r * (a - mean(a) - xh * mean(a*xh)),  a = gamma*ybar,  gammabar = sum(ybar*xh), betabar = sum(ybar)
+// and every quantity is carried as a jet in t (w -> w + t v).  The product rule on jets
+// (common.cuh) yields the tangent and second-order formulas mechanically; per channel only the
+// NEW order's sums have to be reduced in each pass, lower orders are re-read from the plan.
+//
+// Two kernels per direction: a per-channel reduction (grid = C x splits, fp64 atomics) and an
+// elementwise apply (grid = C x chunks).  Both are HBM/L2-bandwidth bound.
+#include "kernels.h"
+
+namespace b2s {
+
+
+template <int K>
+struct BnChan {
+    Jet<K, float> mu, r, gam, bet;
+};
+// plain-float mirror kept in shared memory (shared variables cannot have constructors)
+struct BnChanRaw { float v[4][3]; };
+template <int K>
+__device__ __forceinline__ void to_raw(const BnChan<K>& ch, BnChanRaw& r) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.v[0][k] = ch.mu.c[k]; r.v[1][k] = ch.r.c[k]; r.v[2][k] = ch.gam.c[k]; r.v[3][k] = ch.bet.c[k]; }
+}
+template <int K>
+__device__ __forceinline__ BnChan<K> from_raw(const BnChanRaw& r) {
+    BnChan<K> ch;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ch.mu.c[k] = r.v[0][k]; ch.r.c[k] = r.v[1][k]; ch.gam.c[k] = r.v[2][k]; ch.bet.c[k] = r.v[3][k]; }
+    return ch;
+}
+
+template <int K>
+__device__ inline BnChan<K> bn_channel(const BnArgs& a, int c) {
+    BnChan<K> ch;
+    const double N = (double)a.count;
+    double mu[3] = {0, 0, 0}, s[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+        mu[k] = a.fsum[k][0 * a.C + c] / N;
+        s[k] = a.fsum[k][1 * a.C + c] / N;
+    }
+    s[0] = s[0] - mu[0] * mu[0];
+    if (s[0] < 0) s[0] = 0;
+    Jet<K, double> sj(s[0] + (double)a.eps, s[1], s[2]);
+    Jet<K, double> rj = jet_rsqrt(sj);
+    ch.mu = Jet<K, float>((float)mu[0], (float)mu[1], (float)mu[2]);
+    ch.r = Jet<K, float>((float)rj.c[0], (float)rj.c[1], (float)rj.c[2]);
+    ch.gam = Jet<K, float>(a.gamma[c], (K >= 1 && a.vgamma) ? a.vgamma[c] : 0.f, 0.f);
+    ch.bet = Jet<K, float>(a.beta[c], (K >= 1 && a.vbeta) ? a.vbeta[c] : 0.f, 0.f);
+    return ch;
+}
+
+template <int K>
+__device__ __forceinline__ Jet<K, float> load_jet(const float* const* p, long long idx) {
+    Jet<K, float> j;
+    j.c[0] = p[0][idx];
+    if (K >= 1) j.c[1] = p[1] ? p[1][idx] : 0.f;
+    if (K >= 2) j.c[2] = p[2] ? p[2][idx] : 0.f;
+    return j;
+}
+
+// ---- forward statistics --------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) {
+    __shared__ double red[64];
+    const int c = blockIdx.x;
+    const long long total = (long long)a.batch * a.HW;
+    const double N = (double)a.count;
+    float mu0 = 0.f, mu1 = 0.f;
+    if (K >= 1) mu0 = (float)(a.fsum[0][0 * a.C + c] / N);
+    if (K >= 2) mu1 = (float)(a.fsum[1][0 * a.C + c] / N);
+    double T = 0, Q = 0;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.y * blockDim.x) {
+        const int n = (int)(i / a.HW);
+        const int pix = (int)(i - (long long)n * a.HW);
+        const long long idx = (long long)n * a.in_sstride + (long long)c * a.HW + pix;
+        if (K == 0) {
+            const float x0 = a.x[0][idx];
+            T += x0;
+            Q += (double)x0 * x0;
+        } else if (K == 1) {
+            const float x0 = a.x[0][idx], x1 = a.x[1][idx];
+            T += x1;
+            Q += 2.0 * (double)((x0 - mu0) * x1);
+        } else {
+            const float x0 = a.x[0][idx], x1 = a.x[1][idx], x2 = a.x[2][idx];
+            const float c1 = x1 - mu1;
+            T += x2;
+            Q += 2.0 * (double)(c1 * c1 + (x0 - mu0) * x2);
+        }
+    }
+    double v[2] = {T, Q};
+    block_sum<2, double>(v, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(a.fsum[K] + 0 * a.C + c, v[0]);
+        atomicAdd(a.fsum[K] + 1 * a.C + c, v[1]);
+    }
+}
+
+// ---- forward apply -------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) {
+    __shared__ BnChanRaw sch;
+    const int c = blockIdx.x;
+    if (threadIdx.x == 0) {
+        to_raw<K>(bn_channel<K>(a, c), sch);
+        if (K == 0 && blockIdx.y == 0 && a.running_mean) {
+            const double N = (double)a.count;
+            const double mu = a.fsum[0][0 * a.C + c] / N;
+            double var = a.fsum[0][1 * a.C + c] / N - mu * mu;
+            if (var < 0) var = 0;
+            const double unb = N > 1 ? var * N / (N - 1) : var;
+            const double m = (double)a.momentum;
+            a.running_mean[c] = (float)((1.0 - m) * (double)a.running_mean[c] + m * mu);
+            a.running_var[c] = (float)((1.0 - m) * (double)a.running_var[c] + m * unb);
+        }
+    }
+    __syncthreads();
+    const BnChan<K> ch = from_raw<K>(sch);
+    const long long total = (long long)a.batch * a.HW;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.y * blockDim.x) {
+        const int n = (int)(i / a.HW);
+        const int pix = (int)(i - (long long)n * a.HW);
+        const long long off = (long long)c * a.HW + pix;
+        const long long ii = (long long)n * a.in_sstride + off;
+        const long long oi = (long long)n * a.out_sstride + off;
+        const Jet<K, float> x = load_jet<K>(a.x, ii);
+        const Jet<K, float> xh = (x - ch.mu) * ch.r;
+        const Jet<K, float> y = ch.gam * xh + ch.bet;
+        float out = y.c[K];
+        if (a.relu) {
+            if (K == 0) out = out > 0.f ? out : 0.f;
+            else out = a.y0[oi] > 0.f ? out : 0.f;
+        }
+        a.yk[oi] = out;
+    }
+}
+
+// ---- backward statistics: G_K = sum g_K, X_K = sum (g*xh)_K ----------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) {
+    __shared__ double red[64];
+    __shared__ BnChanRaw sch;
+    const int c = blockIdx.x;
+    if (threadIdx.x == 0) to_raw<K>(bn_channel<K>(a, c), sch);
+    __syncthreads();
+    const BnChan<K> ch = from_raw<K>(sch);
+    const long long total = (long long)a.batch * a.HW;
+    double G = 0, X = 0;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.y * blockDim.x) {
+        const int n = (int)(i / a.HW);
+        const int pix = (int)(i - (long long)n * a.HW);
+        const long long off = (long long)c * a.HW + pix;
+        const long long ii = (long long)n * a.in_sstride + off;
+        const long long oi = (long long)n * a.out_sstride + off;
+        if (a.relu && !(a.y0[oi] > 0.f)) continue;
+        const Jet<K, float> x = load_jet<K>(a.x, ii);
+        const Jet<K, float> xh = (x - ch.mu) * ch.r;
+        const Jet<K, float> g = load_jet<K>(a.g, oi);
+        G += g.c[K];
+        X += (g * xh).c[K];
+    }
+    double v[2] = {G, X};
+    block_sum<2, double>(v, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(a.bsum[K] + 0 * a.C + c, v[0]);
+        atomicAdd(a.bsum[K] + 1 * a.C + c, v[1]);
+    }
+}
+
+// ---- backward apply: xbar_K and the parameter-gradient slices ----------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float pgrad_scale) {
+    __shared__ BnChanRaw sch;
+    __shared__ float sm[2][3];
+    const int c = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const BnChan<K> ch0 = bn_channel<K>(a, c);
+        to_raw<K>(ch0, sch);
+        const double N = (double)a.count;
+        Jet<K, float> Gj, Xj;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+            Gj.c[k] = (float)(a.bsum[k][0 * a.C + c] / N);
+            Xj.c[k] = (float)(a.bsum[k][1 * a.C + c] / N);
+        }
+        const Jet<K, float> t1 = ch0.gam * Gj, t2 = ch0.gam * Xj;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sm[0][k] = t1.c[k]; sm[1][k] = t2.c[k]; }
+        if (blockIdx.y == 0) {
+            atomicAdd(a.out_beta + c, (float)(a.bsum[K][0 * a.C + c] * (double)pgrad_scale));
+            atomicAdd(a.out_gamma + c, (float)(a.bsum[K][1 * a.C + c] * (double)pgrad_scale));
+        }
+    }
+    __syncthreads();
+    if (a.xbar == nullptr) return;
+    const BnChan<K> ch = from_raw<K>(sch);
+    Jet<K, float> m1, m2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m1.c[k] = sm[0][k]; m2.c[k] = sm[1][k]; }
+    const long long total = (long long)a.batch * a.HW;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.y * blockDim.x) {
+        const int n = (int)(i / a.HW);
+        const int pix = (int)(i - (long long)n * a.HW);
+        const long long off = (long long)c * a.HW + pix;
+        const long long ii = (long long)n * a.in_sstride + off;
+        const long long oi = (long long)n * a.out_sstride + off;
+        const Jet<K, float> x = load_jet<K>(a.x, ii);
+        const Jet<K, float> xh = (x - ch.mu) * ch.r;
+        Jet<K, float> g;
+        if (!a.relu || a.y0[oi] > 0.f) g = load_jet<K>(a.g, oi);
+        const Jet<K, float> u = ch.gam * g - m1 - xh * m2;
+        const Jet<K, float> xb = ch.r * u;
+        float out = xb.c[K];
+        if (a.accumulate) out += a.xbar[ii];
+        a.xbar[ii] = out;
+    }
+}
+
+static inline dim3 bn_grid(const BnArgs& a) {
+    const long long total = (long long)a.batch * a.HW;
+    long long splits = (total + 256 * 8 - 1) / (256 * 8);
+    long long cap = (8LL * kNumSMs + a.C - 1) / a.C;
+    if (splits > cap) splits = cap;
+    if (splits < 1) splits = 1;
+    return dim3((unsigned)a.C, (unsigned)splits);
+}
+
+int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a) {
+    const dim3 grid = bn_grid(a);
+    if (order == 0) bn_fwd_stats_kernel<0><<<grid, 256, 0, st>>>(a);
+    else if (order == 1) bn_fwd_stats_kernel<1><<<grid, 256, 0, st>>>(a);
+    else bn_fwd_stats_kernel<2><<<grid, 256, 0, st>>>(a);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a) {
+    const dim3 grid = bn_grid(a);
+    if (order == 0) bn_fwd_apply_kernel<0><<<grid, 256, 0, st>>>(a);
+    else if (order == 1) bn_fwd_apply_kernel<1><<<grid, 256, 0, st>>>(a);
+    else bn_fwd_apply_kernel<2><<<grid, 256, 0, st>>>(a);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a) {
+    const dim3 grid = bn_grid(a);
+    if (order == 0) bn_bwd_stats_kernel<0><<<grid, 256, 0, st>>>(a);
+    else if (order == 1) bn_bwd_stats_kernel<1><<<grid, 256, 0, st>>>(a);
+    else bn_bwd_stats_kernel<2><<<grid, 256, 0, st>>>(a);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+int launch_bn_bwd_apply(cudaStream_t st, int order, const BnArgs& a) {
+    const dim3 grid = bn_grid(a);
+    const float ps = a.pgrad_scale;
+    if (order == 0) bn_bwd_apply_kernel<0><<<grid, 256, 0, st>>>(a, ps);
+    else if (order == 1) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(a, ps);
+    else bn_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(a, ps);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace b2s

@@ -1,0 +1,409 @@
+// conv.cu -- implicit-GEMM Conv2d / Linear jet contractions (fp32 SIMT path).
+//
+// One templated tile kernel serves the three contractions a Conv2d/Linear layer needs at
+// every jet order (math spec rop.py:83-98,115-164):
+//   forward   ydot  = conv(xdot, W) + conv(x, V)                (K-concatenated "pairs")
+//   dgrad     Rxbar = conv^T(Rybar, W) + conv^T(ybar, V)
+//   wgrad     RWbar = corr(x, Rybar) + corr(xdot, ybar)         -> Hv slice of this layer
+// Instead of three separate library calls per term (what autograd issues, opt.py:99,132,143),
+// up to three (activation, weight) pairs are contracted in ONE launch into one accumulator,
+// so every output element is written once.  Layout is NCHW with an explicit per-sample
+// stride so channel-concatenated DenseNet features are addressed in place.
+//
+// This is the fp32-exact CUDA-core path (parity tolerance rtol 1e-4 leaves no room for
+// single-pass TF32).  GEMM view:
+//   forward / dgrad:  M = destination channels, N = batch*pixels, K = source channels*KH*KW
+//   wgrad:            M = Cout, N = Cin*KH*KW, K = batch*pixels (split across blockIdx.z)
+#include "kernels.h"
+
+namespace b2s {
+
+struct ConvKArgs {
+    ConvGeom g;
+    const float* act[kMaxPairs];   // gather source (forward: x-like; dgrad: ybar-like; wgrad: x-like)
+    const float* wt[kMaxPairs];    // weights (forward/dgrad) or adjoint (wgrad)
+    float scale[kMaxPairs];
+    int npairs;
+    const float* bias;
+    const float* relu_ref;
+    int relu_mode;
+    float* out;
+    int accumulate;
+    int k_chunk;                   // wgrad: K elements per blockIdx.z
+};
+
+enum { MODE_FWD = 0, MODE_DGRAD = 1 };
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int TM, int TN, int MODE>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_gather_gemm_kernel(const ConvKArgs a) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int TXN = BN / TN;
+    static_assert(NT % BN == 0, "thread count must be a multiple of BN");
+    static_assert(NT % BK == 0, "thread count must be a multiple of BK");
+    constexpr int B_ROWS = NT / BN;          // k rows of the B tile loaded per pass
+    constexpr int A_ROWS = NT / BK;          // m rows of the A tile loaded per pass
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+
+    const ConvGeom& g = a.g;
+    // destination / source roles
+    const int Cd = MODE == MODE_FWD ? g.Cout : g.Cin;
+    const int Hd = MODE == MODE_FWD ? g.OH : g.H;
+    const int Wd = MODE == MODE_FWD ? g.OW : g.W;
+    const long long d_ss = MODE == MODE_FWD ? g.out_sstride : g.in_sstride;
+    const int Cs = MODE == MODE_FWD ? g.Cin : g.Cout;
+    const int Hs = MODE == MODE_FWD ? g.H : g.OH;
+    const int Ws = MODE == MODE_FWD ? g.W : g.OW;
+    const long long s_ss = MODE == MODE_FWD ? g.in_sstride : g.out_sstride;
+    const int KHW = g.KH * g.KW;
+    const int Ktot = Cs * KHW;
+    const int HWd = Hd * Wd;
+    const long long J = (long long)g.batch * HWd;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TXN, ty = tid / TXN;
+    const int m0 = blockIdx.y * BM;
+    const long long j0 = (long long)blockIdx.x * BN;
+
+    // this thread's pixel for the B-tile loads
+    const int jb = tid % BN;
+    const int kb0 = tid / BN;
+    const long long jl = j0 + jb;
+    const bool j_ok = jl < J;
+    int n_l = 0, y_l = 0, x_l = 0;
+    if (j_ok) {
+        n_l = (int)(jl / HWd);
+        int pix = (int)(jl - (long long)n_l * HWd);
+        y_l = pix / Wd;
+        x_l = pix - y_l * Wd;
+    }
+    const int ka = tid % BK;
+    const int ma0 = tid / BK;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int p = 0; p < a.npairs; ++p) {
+        const float* __restrict__ src = a.act[p] + (long long)n_l * s_ss;
+        const float* __restrict__ wt = a.wt[p];
+        const float sc = a.scale[p];
+        for (int k0 = 0; k0 < Ktot; k0 += BK) {
+            // ---- A tile: weights
+#pragma unroll
+            for (int i = 0; i < BM / A_ROWS; ++i) {
+                const int mb = ma0 + i * A_ROWS;
+                const int m = m0 + mb, k = k0 + ka;
+                float v = 0.f;
+                if (m < Cd && k < Ktot) {
+                    if (MODE == MODE_FWD) {
+                        v = wt[(long long)m * Ktot + k];
+                    } else {
+                        const int c = k / KHW, t = k - c * KHW;       // c = output channel of the conv
+                        v = wt[((long long)c * g.Cin + m) * KHW + t];
+                    }
+                }
+                As[ka][mb] = v * sc;
+            }
+            // ---- B tile: gathered activations
+#pragma unroll
+            for (int i = 0; i < BK / B_ROWS; ++i) {
+                const int kb = kb0 + i * B_ROWS;
+                const int k = k0 + kb;
+                float v = 0.f;
+                if (j_ok && k < Ktot) {
+                    int c, ky, kx;
+                    if (KHW == 1) { c = k; ky = 0; kx = 0; }
+                    else { c = k / KHW; const int t = k - c * KHW; ky = t / g.KW; kx = t - ky * g.KW; }
+                    int sy, sx;
+                    bool ok;
+                    if (MODE == MODE_FWD) {
+                        sy = y_l * g.sh + ky - g.ph;
+                        sx = x_l * g.sw + kx - g.pw;
+                        ok = sy >= 0 && sy < Hs && sx >= 0 && sx < Ws;
+                    } else {
+                        const int ty_ = y_l + g.ph - ky, tx_ = x_l + g.pw - kx;
+                        ok = ty_ >= 0 && tx_ >= 0;
+                        sy = ty_ / g.sh; sx = tx_ / g.sw;
+                        ok = ok && (sy * g.sh == ty_) && (sx * g.sw == tx_) && sy < Hs && sx < Ws;
+                    }
+                    if (ok) v = src[((long long)c * Hs + sy) * Ws + sx];
+                }
+                Bs[kb][jb] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float av[TM], bv[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx + j * TXN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const long long jj = j0 + tx + j * TXN;
+        if (jj >= J) continue;
+        const int n = (int)(jj / HWd);
+        const int pix = (int)(jj - (long long)n * HWd);
+        const long long base = (long long)n * d_ss + pix;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int m = m0 + ty * TM + i;
+            if (m >= Cd) continue;
+            const long long o = base + (long long)m * HWd;
+            float v = acc[i][j];
+            if (a.bias) v += a.bias[m];
+            if (a.accumulate) v += a.out[o];
+            if (a.relu_mode == 1) v = v > 0.f ? v : 0.f;
+            else if (a.relu_mode == 2) v = a.relu_ref[o] > 0.f ? v : 0.f;
+            a.out[o] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: Wbar[m, (c,ky,kx)] += sum_j adj[n, m, oy, ox] * act[n, c, oy*sh+ky-ph, ox*sw+kx-pw]
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_wgrad_kernel(const ConvKArgs a) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int TXN = BN / TN;
+    static_assert(NT % BK == 0, "thread count must be a multiple of BK");
+    constexpr int ROWS = NT / BK;            // rows (m or n) loaded per pass
+    constexpr int A_IT = (BM + ROWS - 1) / ROWS, B_IT = (BN + ROWS - 1) / ROWS;
+    __shared__ float As[BK][BM + 1];
+    __shared__ float Bs[BK][BN + 1];
+
+    const ConvGeom& g = a.g;
+    const int KHW = g.KH * g.KW;
+    const int Ncol = g.Cin * KHW;
+    const int OHW = g.OH * g.OW;
+    const long long J = (long long)g.batch * OHW;
+    const long long jbeg = (long long)blockIdx.z * a.k_chunk;
+    const long long jend = jbeg + a.k_chunk < J ? jbeg + a.k_chunk : J;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TXN, ty = tid / TXN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int jb = tid % BK, r0 = tid / BK;
+
+    // decode the tile's B columns once per CTA (reads below are warp-uniform broadcasts)
+    __shared__ int col_off[BN];
+    __shared__ int col_tap[BN];
+    for (int nb = tid; nb < BN; nb += NT) {
+        const int col = n0 + nb;
+        if (col < Ncol) {
+            const int c = col / KHW, t = col - c * KHW;
+            const int ky = t / g.KW, kx = t - ky * g.KW;
+            col_off[nb] = c * g.H * g.W;
+            col_tap[nb] = (ky << 16) | kx;
+        } else {
+            col_off[nb] = -1;
+            col_tap[nb] = 0;
+        }
+    }
+    __syncthreads();
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int p = 0; p < a.npairs; ++p) {
+        const float* __restrict__ act = a.act[p];
+        const float* __restrict__ adj = a.wt[p];
+        const float sc = a.scale[p];
+        for (long long k0 = jbeg; k0 < jend; k0 += BK) {
+            const long long j = k0 + jb;
+            const bool ok = j < jend;
+            int n = 0, oy = 0, ox = 0, pix = 0;
+            if (ok) {
+                n = (int)(j / OHW);
+                pix = (int)(j - (long long)n * OHW);
+                oy = pix / g.OW;
+                ox = pix - oy * g.OW;
+            }
+            const float* __restrict__ adj_n = adj + (long long)n * g.out_sstride + pix;
+            const float* __restrict__ act_n = act + (long long)n * g.in_sstride;
+#pragma unroll
+            for (int i = 0; i < A_IT; ++i) {
+                const int mb = r0 + i * ROWS;
+                if (mb < BM) {
+                    const int m = m0 + mb;
+                    float v = 0.f;
+                    if (ok && m < g.Cout) v = adj_n[(long long)m * OHW] * sc;
+                    As[jb][mb] = v;
+                }
+            }
+            const int iy0 = oy * g.sh - g.ph, ix0 = ox * g.sw - g.pw;
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                const int nb = r0 + i * ROWS;
+                if (nb < BN) {
+                    float v = 0.f;
+                    const int coff = col_off[nb];
+                    if (ok && coff >= 0) {
+                        const int tap = col_tap[nb];
+                        const int sy = iy0 + (tap >> 16), sx = ix0 + (tap & 0xffff);
+                        if (sy >= 0 && sy < g.H && sx >= 0 && sx < g.W) v = act_n[coff + sy * g.W + sx];
+                    }
+                    Bs[jb][nb] = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float av[TM], bv[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+                for (int jn = 0; jn < TN; ++jn) bv[jn] = Bs[kk][tx + jn * TXN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int jn = 0; jn < TN; ++jn) acc[i][jn] = fmaf(av[i], bv[jn], acc[i][jn]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= g.Cout) continue;
+#pragma unroll
+        for (int jn = 0; jn < TN; ++jn) {
+            const int col = n0 + tx + jn * TXN;
+            if (col < Ncol) atomicAdd(a.out + (long long)m * Ncol + col, acc[i][jn]);
+        }
+    }
+}
+
+// bbar[c] += sum over (n, pix) of adj
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ adj, int batch, int C, int HW,
+                                                        long long sstride, float* __restrict__ bbar) {
+    __shared__ float red[32];
+    const int c = blockIdx.x;
+    const long long total = (long long)batch * HW;
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.y * blockDim.x) {
+        const int n = (int)(i / HW);
+        const int pix = (int)(i - (long long)n * HW);
+        s += adj[(long long)n * sstride + (long long)c * HW + pix];
+    }
+    float v[1] = {s};
+    block_sum<1, float>(v, red);
+    if (threadIdx.x == 0) atomicAdd(bbar + c, v[0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
+    const ConvGeom& g = a.g;
+    const int Cd = MODE == MODE_FWD ? g.Cout : g.Cin;
+    const long long J = (long long)g.batch * (MODE == MODE_FWD ? g.OH * g.OW : g.H * g.W);
+    if (Cd <= 16) {
+        dim3 grid(cdiv(J, 256), cdiv(Cd, 16));
+        conv_gather_gemm_kernel<16, 256, 16, 4, 4, MODE><<<grid, 256, 0, st>>>(a);
+    } else if (Cd <= 32) {
+        dim3 grid(cdiv(J, 128), cdiv(Cd, 32));
+        conv_gather_gemm_kernel<32, 128, 16, 4, 4, MODE><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid(cdiv(J, 64), cdiv(Cd, 64));
+        conv_gather_gemm_kernel<64, 64, 16, 4, 4, MODE><<<grid, 256, 0, st>>>(a);
+    }
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_conv_fwd(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* act,
+                    const float* const* wt, const float* scale, const float* bias, int relu_mode,
+                    const float* relu_ref, float* out, int accumulate) {
+    ConvKArgs a{};
+    a.g = g;
+    a.npairs = npairs;
+    for (int p = 0; p < npairs; ++p) { a.act[p] = act[p]; a.wt[p] = wt[p]; a.scale[p] = scale[p]; }
+    a.bias = bias; a.relu_mode = relu_mode; a.relu_ref = relu_ref; a.out = out; a.accumulate = accumulate;
+    return launch_gather<MODE_FWD>(st, a);
+}
+
+int launch_conv_dgrad(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* adj,
+                      const float* const* wt, const float* scale, float* out, int accumulate) {
+    ConvKArgs a{};
+    a.g = g;
+    a.npairs = npairs;
+    for (int p = 0; p < npairs; ++p) { a.act[p] = adj[p]; a.wt[p] = wt[p]; a.scale[p] = scale[p]; }
+    a.bias = nullptr; a.relu_mode = 0; a.relu_ref = nullptr; a.out = out; a.accumulate = accumulate;
+    return launch_gather<MODE_DGRAD>(st, a);
+}
+
+int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* act,
+                      const float* const* adj, const float* scale, float* wbar) {
+    ConvKArgs a{};
+    a.g = g;
+    a.npairs = npairs;
+    for (int p = 0; p < npairs; ++p) { a.act[p] = act[p]; a.wt[p] = adj[p]; a.scale[p] = scale[p]; }
+    a.out = wbar;
+    const int Ncol = g.Cin * g.KH * g.KW;
+    const long long J = (long long)g.batch * g.OH * g.OW;
+    constexpr int BK = 32;
+    const long long ktiles = (J + BK - 1) / BK;
+    auto pick_split = [&](int tiles_mn) {
+        long long want = (4LL * kNumSMs + tiles_mn - 1) / tiles_mn;
+        if (want < 1) want = 1;
+        if (want > ktiles) want = ktiles;
+        long long per = (ktiles + want - 1) / want;     // k tiles per split
+        a.k_chunk = (int)(per * BK);
+        return (int)((ktiles + per - 1) / per);
+    };
+    if (g.Cout <= 16) {
+        const int gm = cdiv(g.Cout, 16), gn = cdiv(Ncol, 256);
+        dim3 grid(gn, gm, pick_split(gm * gn));
+        conv_wgrad_kernel<16, 256, BK, 4, 4><<<grid, 256, 0, st>>>(a);
+    } else if (g.Cout <= 32) {
+        const int gm = cdiv(g.Cout, 32), gn = cdiv(Ncol, 128);
+        dim3 grid(gn, gm, pick_split(gm * gn));
+        conv_wgrad_kernel<32, 128, BK, 4, 4><<<grid, 256, 0, st>>>(a);
+    } else {
+        const int gm = cdiv(g.Cout, 64), gn = cdiv(Ncol, 64);
+        dim3 grid(gn, gm, pick_split(gm * gn));
+        conv_wgrad_kernel<64, 64, BK, 4, 4><<<grid, 256, 0, st>>>(a);
+    }
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_bias_grad(cudaStream_t st, const float* adj, int batch, int C, int HW, long long sstride,
+                     float* bbar) {
+    const long long total = (long long)batch * HW;
+    int splits = (int)((total + 256 * 8 - 1) / (256 * 8));
+    const int cap = (4 * kNumSMs + C - 1) / C;
+    if (splits > cap) splits = cap;
+    if (splits < 1) splits = 1;
+    dim3 grid(C, splits);
+    bias_grad_kernel<<<grid, 256, 0, st>>>(adj, batch, C, HW, sstride, bbar);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace b2s

@@ -1,0 +1,848 @@
+// plan.cu -- tape interpreter + C ABI of libb200spectral.
+//
+// A plan is the static replacement of the autograd graph that the reference rebuilds for every
+// minibatch (HVPOperator.prepare_grad with create_graph=True, opt.py:175-192): the tape of layer
+// ops, the flat-parameter offsets and preallocated caches for every tensor's value jets
+// (x, xdot, xddot) and adjoint jets (xbar, R xbar, R^2 xbar).  One "pass of order k" walks the
+// tape forward then backward propagating the order-k components (rop.py:69-164 generalised):
+//     order 0 -> loss and gradient         (prepare_grad,        opt.py:175-192)
+//     order 1 -> Hessian-vector product    (Hv,                  opt.py:77-108)
+//     order 2 -> grad_w (v^T H v)          (second half of vGHv, opt.py:110-152)
+// Each pass is a fixed kernel sequence, captured once per batch size into a CUDA graph and
+// replayed (one graph launch per HVP instead of the reference's per-op autograd dispatch).
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_spectral.h"
+#include "comm.h"
+#include "kernels.h"
+#include "vec.h"
+
+namespace b2s {
+
+// ---- error / counters ---------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static long long g_launch_total = 0;
+static std::mutex g_launch_mu;
+thread_local long long g_launches = 0;
+static thread_local bool g_counting_paused = false;
+static thread_local long long g_capture_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) {
+    g_capture_count += n;
+    if (g_counting_paused) return;
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    g_launch_total += n;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+struct b2s_pistate {
+    int device = 0;
+    long long n = 0;
+    int cap = 0;
+    PiDev h{};               // host mirror used to initialise the device copy
+    PiDev* d = nullptr;
+    double* vbuf[2] = {nullptr, nullptr};
+    double* rbuf[2] = {nullptr, nullptr};
+    float* v32 = nullptr;
+    double* alpha = nullptr;
+    double* traj = nullptr;
+    double* scratch = nullptr;
+    bool have_alpha = false;
+    bool own_v32 = true;     // false: v32 aliases the owning plan's tangent-direction buffer
+};
+
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    long long kernels = 0;
+};
+
+struct b2s_plan {
+    int device = 0;
+    cudaStream_t caller = nullptr;    // stream the caller's tensors are ordered on
+    cudaStream_t stream = nullptr;    // plan-owned work stream (graphs cannot be captured on stream 0)
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    bool use_graphs = true;
+    std::vector<b2s_tensor> tensors;
+    std::vector<b2s_op> ops;
+    std::vector<long long> buf_elems;
+    std::vector<long long> buf_off;   // element offset of each buffer inside an arena (per max_batch)
+    long long arena_elems = 0;
+    int logits = 0, head = 0;
+    long long P = 0;
+    int max_batch = 0;
+    int batch = 0;                    // batch of the cached base pass
+    double loss_scale = 1.0;
+    long long workspace = 0;
+
+    float* fw[3] = {nullptr, nullptr, nullptr};   // value jets
+    float* bw[3] = {nullptr, nullptr, nullptr};   // adjoint jets
+    float* params = nullptr;
+    float* v32 = nullptr;             // tangent direction (fp32 rounding of v)
+    float* out32[3] = {nullptr, nullptr, nullptr};
+    double* loss = nullptr;
+
+    // batch norm
+    int n_bn = 0;
+    std::vector<long long> bn_off;    // per op index: offset (in doubles) of its [2][C] block, -1 if not BN
+    long long bn_total = 0;
+    double* fsum[3] = {nullptr, nullptr, nullptr};
+    double* bsum[3] = {nullptr, nullptr, nullptr};
+    std::vector<float*> bn_rm, bn_rv;
+
+    // max pool
+    std::vector<int32_t*> argmax;     // per op index
+
+    // labels
+    long long* labels = nullptr;
+    float* target = nullptr;
+    float* coef = nullptr;
+    int n_classes = 0;
+
+    std::map<long long, GraphEntry> graphs;   // key = order * 2^32 + batch
+    bool v_is_current = false;        // order-1 caches correspond to the contents of v32
+
+    b2s_pistate* pi = nullptr;
+    Comm* comm = nullptr;
+    int world = 1;
+};
+
+namespace b2s {
+
+static inline float* tptr(const b2s_plan* p, float* const* arena, int order, int t) {
+    const b2s_tensor& T = p->tensors[t];
+    return arena[order] ? arena[order] + p->buf_off[T.buf] + T.offset : nullptr;
+}
+static inline View tview(const b2s_plan* p, float* const* arena, int order, int t) {
+    const b2s_tensor& T = p->tensors[t];
+    View v;
+    v.p = tptr(p, arena, order, t);
+    v.C = T.C; v.H = T.H; v.W = T.W; v.sstride = T.sample_stride;
+    return v;
+}
+
+static int alloc_order(b2s_plan* p, int k) {
+    if (p->fw[k]) return 0;
+    const size_t bytes = (size_t)p->arena_elems * sizeof(float);
+    B2S_CUDA(cudaMalloc(&p->fw[k], bytes));
+    B2S_CUDA(cudaMalloc(&p->bw[k], bytes));
+    B2S_CUDA(cudaMemset(p->fw[k], 0, bytes));
+    B2S_CUDA(cudaMemset(p->bw[k], 0, bytes));
+    B2S_CUDA(cudaMalloc(&p->out32[k], (size_t)(p->P + 4) * sizeof(float)));
+    p->workspace += 2 * (long long)bytes + (p->P + 4) * 4;
+    if (p->bn_total > 0) {
+        B2S_CUDA(cudaMalloc(&p->fsum[k], (size_t)p->bn_total * sizeof(double)));
+        B2S_CUDA(cudaMalloc(&p->bsum[k], (size_t)p->bn_total * sizeof(double)));
+        p->workspace += 2 * p->bn_total * 8;
+    }
+    return 0;
+}
+
+static ConvGeom conv_geom(const b2s_plan* p, const b2s_op& op) {
+    const b2s_tensor& I = p->tensors[op.in];
+    const b2s_tensor& O = p->tensors[op.out];
+    ConvGeom g;
+    g.batch = p->batch;
+    g.Cin = I.C; g.H = I.H; g.W = I.W; g.in_sstride = I.sample_stride;
+    g.Cout = O.C; g.OH = O.H; g.OW = O.W; g.out_sstride = O.sample_stride;
+    g.KH = op.kh; g.KW = op.kw; g.sh = op.sh; g.sw = op.sw; g.ph = op.ph; g.pw = op.pw;
+    return g;
+}
+
+static BnArgs bn_args(b2s_plan* p, int oi, int K) {
+    const b2s_op& op = p->ops[oi];
+    const b2s_tensor& I = p->tensors[op.in];
+    const b2s_tensor& O = p->tensors[op.out];
+    const bool first = op.flags & B2S_F_FIRST;
+    BnArgs a{};
+    a.batch = p->batch; a.C = I.C; a.HW = I.H * I.W;
+    a.in_sstride = I.sample_stride; a.out_sstride = O.sample_stride;
+    for (int k = 0; k < 3; ++k) {
+        a.x[k] = (k <= K && (k == 0 || !first)) ? tptr(p, p->fw, k, op.in) : nullptr;
+        a.g[k] = k <= K ? tptr(p, p->bw, k, op.out) : nullptr;
+        a.fsum[k] = p->fsum[k] ? p->fsum[k] + p->bn_off[oi] : nullptr;
+        a.bsum[k] = p->bsum[k] ? p->bsum[k] + p->bn_off[oi] : nullptr;
+    }
+    a.y0 = tptr(p, p->fw, 0, op.out);
+    a.yk = tptr(p, p->fw, K, op.out);
+    a.xbar = first ? nullptr : tptr(p, p->bw, K, op.in);
+    a.gamma = p->params + op.w_off; a.beta = p->params + op.b_off;
+    a.vgamma = p->v32 + op.w_off; a.vbeta = p->v32 + op.b_off;
+    a.out_gamma = p->out32[K] + op.w_off; a.out_beta = p->out32[K] + op.b_off;
+    a.running_mean = op.slot >= 0 && op.slot < (int)p->bn_rm.size() ? p->bn_rm[op.slot] : nullptr;
+    a.running_var = op.slot >= 0 && op.slot < (int)p->bn_rv.size() ? p->bn_rv[op.slot] : nullptr;
+    a.eps = op.eps; a.momentum = op.momentum;
+    a.relu = (op.flags & B2S_F_RELU) ? 1 : 0;
+    a.first = first ? 1 : 0;
+    a.count = (long long)p->batch * p->world * a.HW;
+    a.accumulate = (op.flags & B2S_F_BWD_ACC) ? 1 : 0;
+    a.pgrad_scale = 1.0f / (float)p->world;
+    return a;
+}
+
+// ---- forward sweep of order K -----------------------------------------------------------------
+static int forward(b2s_plan* p, int K) {
+    cudaStream_t st = p->stream;
+    if (p->bn_total > 0) B2S_CUDA(cudaMemsetAsync(p->fsum[K], 0, (size_t)p->bn_total * sizeof(double), st));
+    for (size_t oi = 0; oi < p->ops.size(); ++oi) {
+        const b2s_op& op = p->ops[oi];
+        const bool first = op.flags & B2S_F_FIRST;
+        const bool relu = op.flags & B2S_F_RELU;
+        switch (op.kind) {
+        case B2S_OP_CONV: {
+            const ConvGeom g = conv_geom(p, op);
+            const float* W = p->params + op.w_off;
+            const float* V = p->v32 + op.w_off;
+            const float* act[kMaxPairs];
+            const float* wt[kMaxPairs];
+            float sc[kMaxPairs];
+            int np = 0;
+            const float* bias = nullptr;
+            float* out = tptr(p, p->fw, K, op.out);
+            const float* y0 = tptr(p, p->fw, 0, op.out);
+            if (K == 0) {
+                act[np] = tptr(p, p->fw, 0, op.in); wt[np] = W; sc[np] = 1.f; ++np;
+                if (op.b_off >= 0) bias = p->params + op.b_off;
+            } else if (K == 1) {
+                if (!first) { act[np] = tptr(p, p->fw, 1, op.in); wt[np] = W; sc[np] = 1.f; ++np; }
+                act[np] = tptr(p, p->fw, 0, op.in); wt[np] = V; sc[np] = 1.f; ++np;
+                if (op.b_off >= 0) bias = p->v32 + op.b_off;
+            } else {
+                if (first) {   // x has no tangent: yddot = 0
+                    B2S_TRY(launch_zero_view(st, tview(p, p->fw, 2, op.out), p->batch));
+                    break;
+                }
+                act[np] = tptr(p, p->fw, 2, op.in); wt[np] = W; sc[np] = 1.f; ++np;
+                act[np] = tptr(p, p->fw, 1, op.in); wt[np] = V; sc[np] = 2.f; ++np;
+            }
+            B2S_TRY(launch_conv_fwd(st, g, np, act, wt, sc, bias, relu ? (K == 0 ? 1 : 2) : 0, y0, out, 0));
+            break;
+        }
+        case B2S_OP_BN: {
+            const BnArgs a = bn_args(p, (int)oi, K);
+            if (!(first && K > 0)) {
+                B2S_TRY(launch_bn_fwd_stats(st, K, a));
+                if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.fsum[K], 2 * a.C, st));
+            }
+            B2S_TRY(launch_bn_fwd_apply(st, K, a));
+            break;
+        }
+        case B2S_OP_RELU:
+            B2S_TRY(launch_relu_fwd(st, K, tview(p, p->fw, 0, op.in), tview(p, p->fw, K, op.in),
+                                    tview(p, p->fw, K, op.out), p->batch));
+            break;
+        case B2S_OP_MAXPOOL:
+            B2S_TRY(launch_maxpool_fwd(st, K, tview(p, p->fw, K, op.in), tview(p, p->fw, K, op.out),
+                                       p->argmax[oi], p->batch, op.kh, op.kw, op.sh, op.sw, op.ph, op.pw));
+            break;
+        case B2S_OP_AVGPOOL:
+            B2S_TRY(launch_avgpool_fwd(st, tview(p, p->fw, K, op.in), tview(p, p->fw, K, op.out), p->batch,
+                                       op.kh));
+            break;
+        case B2S_OP_COPY:
+            B2S_TRY(launch_copy_view(st, tview(p, p->fw, K, op.in), tview(p, p->fw, K, op.out), p->batch, 0));
+            break;
+        default:
+            set_error("unknown op kind %d", op.kind);
+            return -5;
+        }
+    }
+    // loss head
+    const b2s_tensor& L = p->tensors[p->logits];
+    HeadArgs h{};
+    h.kind = p->head; h.batch = p->batch; h.C = L.C * L.H * L.W;
+    for (int k = 0; k < 3; ++k) h.z[k] = k <= K ? tptr(p, p->fw, k, p->logits) : nullptr;
+    h.zs = L.sample_stride;
+    h.labels = p->labels; h.target = p->target; h.coef = p->coef;
+    h.loss_scale = p->loss_scale;
+    h.zbar = tptr(p, p->bw, K, p->logits);
+    h.loss = K == 0 ? p->loss : nullptr;
+    if (K == 0) B2S_CUDA(cudaMemsetAsync(p->loss, 0, sizeof(double), st));
+    B2S_TRY(launch_head(st, K, h));
+    return 0;
+}
+
+// ---- backward sweep of order K ----------------------------------------------------------------
+static int backward(b2s_plan* p, int K) {
+    cudaStream_t st = p->stream;
+    B2S_CUDA(cudaMemsetAsync(p->out32[K], 0, (size_t)p->P * sizeof(float), st));
+    if (p->bn_total > 0) B2S_CUDA(cudaMemsetAsync(p->bsum[K], 0, (size_t)p->bn_total * sizeof(double), st));
+    for (int oi = (int)p->ops.size() - 1; oi >= 0; --oi) {
+        const b2s_op& op = p->ops[oi];
+        const bool first = op.flags & B2S_F_FIRST;
+        const bool relu = op.flags & B2S_F_RELU;
+        const int acc = (op.flags & B2S_F_BWD_ACC) ? 1 : 0;
+        switch (op.kind) {
+        case B2S_OP_CONV: {
+            const ConvGeom g = conv_geom(p, op);
+            if (relu) B2S_TRY(launch_mask_inplace(st, tview(p, p->fw, 0, op.out), tview(p, p->bw, K, op.out), p->batch));
+            const float* W = p->params + op.w_off;
+            const float* V = p->v32 + op.w_off;
+            const float* x[3];
+            const float* gk[3];
+            for (int k = 0; k < 3; ++k) {
+                x[k] = k <= K ? tptr(p, p->fw, k, op.in) : nullptr;
+                gk[k] = k <= K ? tptr(p, p->bw, k, op.out) : nullptr;
+            }
+            const float* a_[kMaxPairs];
+            const float* b_[kMaxPairs];
+            float sc[kMaxPairs];
+            int np = 0;
+            // weight gradient of order K:  sum_j binom(K,j) corr(x_j, g_{K-j})
+            a_[np] = x[0]; b_[np] = gk[K]; sc[np] = 1.f; ++np;
+            if (!first && K >= 1) { a_[np] = x[1]; b_[np] = gk[K - 1]; sc[np] = K == 2 ? 2.f : 1.f; ++np; }
+            if (!first && K == 2) { a_[np] = x[2]; b_[np] = gk[0]; sc[np] = 1.f; ++np; }
+            B2S_TRY(launch_conv_wgrad(st, g, np, a_, b_, sc, p->out32[K] + op.w_off));
+            if (op.b_off >= 0)
+                B2S_TRY(launch_bias_grad(st, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
+                                         p->out32[K] + op.b_off));
+            if (!first) {
+                np = 0;
+                a_[np] = gk[K]; b_[np] = W; sc[np] = 1.f; ++np;
+                if (K >= 1) { a_[np] = gk[K - 1]; b_[np] = V; sc[np] = K == 2 ? 2.f : 1.f; ++np; }
+                B2S_TRY(launch_conv_dgrad(st, g, np, a_, b_, sc, tptr(p, p->bw, K, op.in), acc));
+            }
+            break;
+        }
+        case B2S_OP_BN: {
+            const BnArgs a = bn_args(p, oi, K);
+            B2S_TRY(launch_bn_bwd_stats(st, K, a));
+            if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.bsum[K], 2 * a.C, st));
+            B2S_TRY(launch_bn_bwd_apply(st, K, a));
+            break;
+        }
+        case B2S_OP_RELU:
+            if (!first)
+                B2S_TRY(launch_relu_bwd(st, tview(p, p->fw, 0, op.in), tview(p, p->bw, K, op.out),
+                                        tview(p, p->bw, K, op.in), p->batch, acc));
+            break;
+        case B2S_OP_MAXPOOL:
+            if (!first) {
+                if (!acc) B2S_TRY(launch_zero_view(st, tview(p, p->bw, K, op.in), p->batch));
+                B2S_TRY(launch_maxpool_bwd(st, tview(p, p->bw, K, op.out), tview(p, p->bw, K, op.in),
+                                           p->argmax[oi], p->batch));
+            }
+            break;
+        case B2S_OP_AVGPOOL:
+            if (!first)
+                B2S_TRY(launch_avgpool_bwd(st, tview(p, p->bw, K, op.out), tview(p, p->bw, K, op.in), p->batch,
+                                           op.kh, acc));
+            break;
+        case B2S_OP_COPY:
+            if (!first)
+                B2S_TRY(launch_copy_view(st, tview(p, p->bw, K, op.out), tview(p, p->bw, K, op.in), p->batch, acc));
+            break;
+        default:
+            set_error("unknown op kind %d", op.kind);
+            return -5;
+        }
+    }
+    if (p->comm) B2S_TRY(comm_allreduce_f32(p->comm, p->out32[K], p->P, st));
+    return 0;
+}
+
+static int run_pass_eager(b2s_plan* p, int K) {
+    B2S_TRY(forward(p, K));
+    B2S_TRY(backward(p, K));
+    return 0;
+}
+
+// one pass of order K on p->stream, through a CUDA graph when enabled
+static int run_pass(b2s_plan* p, int K) {
+    B2S_TRY(alloc_order(p, K));
+    if (!p->use_graphs) return run_pass_eager(p, K);
+    const long long key = ((long long)K << 32) | (unsigned)p->batch;
+    auto it = p->graphs.find(key);
+    if (it == p->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        g_counting_paused = true;
+        g_capture_count = 0;
+        cudaError_t e = cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            g_counting_paused = false;
+            set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+            return -2;
+        }
+        const int rc = run_pass_eager(p, K);
+        e = cudaStreamEndCapture(p->stream, &graph);
+        g_counting_paused = false;
+        if (rc != 0) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) {
+            set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            return -2;
+        }
+        GraphEntry ge;
+        ge.kernels = g_capture_count;
+        e = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            return -2;
+        }
+        it = p->graphs.emplace(key, ge).first;
+    }
+    B2S_CUDA(cudaGraphLaunch(it->second.exec, p->stream));
+    count_launch((int)it->second.kernels);
+    return 0;
+}
+
+// order the plan stream after the caller's stream / the caller's stream after the plan stream
+static int enter(b2s_plan* p) {
+    B2S_CUDA(cudaSetDevice(p->device));
+    B2S_CUDA(cudaEventRecord(p->ev_in, p->caller));
+    B2S_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in, 0));
+    return 0;
+}
+static int leave(b2s_plan* p) {
+    B2S_CUDA(cudaEventRecord(p->ev_out, p->stream));
+    B2S_CUDA(cudaStreamWaitEvent(p->caller, p->ev_out, 0));
+    return 0;
+}
+
+static int pi_upload(b2s_pistate* s, cudaStream_t st) {
+    B2S_CUDA(cudaMemcpyAsync(s->d, &s->h, sizeof(PiDev), cudaMemcpyHostToDevice, st));
+    // the host mirror may be rewritten right after this call returns
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int pi_reset_impl(b2s_pistate* s, const double* d_v0, const b2s_power_cfg* cfg, cudaStream_t st) {
+    if (cfg->max_iter > s->cap) {
+        set_error("power iteration: max_iter %d exceeds the state's capacity %d", cfg->max_iter, s->cap);
+        return -6;
+    }
+    B2S_CUDA(cudaMemcpyAsync(s->vbuf[0], d_v0, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2S_TRY(launch_cast_f64_f32(st, s->vbuf[0], s->v32, s->n));
+    s->have_alpha = cfg->h_alpha != nullptr;
+    if (s->have_alpha)
+        B2S_CUDA(cudaMemcpyAsync(s->alpha, cfg->h_alpha, (size_t)cfg->max_iter * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+    PiDev& h = s->h;
+    memset(&h, 0, sizeof(h));
+    h.n = s->n;
+    h.vbuf[0] = s->vbuf[0]; h.vbuf[1] = s->vbuf[1];
+    h.rbuf[0] = s->rbuf[0]; h.rbuf[1] = s->rbuf[1];
+    h.v32 = s->v32;
+    h.alpha = s->have_alpha ? s->alpha : nullptr;
+    h.traj = s->traj;
+    h.scratch = s->scratch;
+    h.precond = cfg->precond;
+    h.max_iter = cfg->max_iter;
+    h.last_iter = -1;
+    h.eps = cfg->eps;
+    h.stop[0] = h.stop[1] = h.stop[2] = INFINITY;
+    if (cfg->max_iter <= 0) h.done = 1;
+    return pi_upload(s, st);
+}
+
+static int pi_result_impl(b2s_pistate* s, b2s_power_result* r, double* h_traj, double* d_v_out, cudaStream_t st) {
+    PiDev h;
+    B2S_CUDA(cudaMemcpyAsync(&h, s->d, sizeof(PiDev), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (r) {
+        r->iters = h.last_iter;
+        r->converged = h.converged;
+        r->lam = h.lam; r->norm = h.norm; r->rn = h.rn; r->vnn = h.vnn;
+        for (int k = 0; k < 3; ++k) r->stop[k] = h.stop[k];
+    }
+    if (h_traj && h.last_iter >= 0) {
+        std::vector<double> tmp((size_t)(h.last_iter + 1) * 4);
+        B2S_CUDA(cudaMemcpy(tmp.data(), s->traj, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i <= h.last_iter; ++i) {
+            h_traj[i * 5 + 0] = i;
+            for (int q = 0; q < 4; ++q) h_traj[i * 5 + 1 + q] = tmp[(size_t)i * 4 + q];
+        }
+    }
+    if (d_v_out)
+        B2S_CUDA(cudaMemcpyAsync(d_v_out, s->vbuf[h.cur], (size_t)s->n * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace b2s
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int b2s_abi_version(void) { return B2S_ABI_VERSION; }
+const char* b2s_last_error(void) { return g_err; }
+int64_t b2s_launch_count(void) {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    return g_launch_total;
+}
+
+int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t* buf_elems, int32_t n_bufs,
+                    const b2s_op* ops, int32_t n_ops, int32_t logits, int32_t head, int64_t n_params,
+                    int32_t max_batch, int32_t device, b2s_plan** out) {
+    if (!tensors || !buf_elems || !ops || !out || n_tensors <= 0 || n_bufs <= 0 || n_ops <= 0 || max_batch <= 0) {
+        set_error("b2s_plan_create: invalid arguments");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("b2s_plan_create: no CUDA device is available; this library has no CPU fallback");
+        return -7;
+    }
+    B2S_CUDA(cudaSetDevice(device));
+    b2s_plan* p = new b2s_plan();
+    p->device = device;
+    p->tensors.assign(tensors, tensors + n_tensors);
+    p->ops.assign(ops, ops + n_ops);
+    p->buf_elems.assign(buf_elems, buf_elems + n_bufs);
+    p->logits = logits; p->head = head; p->P = n_params; p->max_batch = max_batch;
+    // validate
+    for (int t = 0; t < n_tensors; ++t) {
+        const b2s_tensor& T = tensors[t];
+        if (T.buf < 0 || T.buf >= n_bufs || T.offset < 0 ||
+            T.offset + (long long)T.C * T.H * T.W > buf_elems[T.buf] || T.sample_stride != buf_elems[T.buf]) {
+            set_error("b2s_plan_create: tensor %d does not fit its buffer", t);
+            delete p;
+            return -1;
+        }
+    }
+    p->buf_off.resize(n_bufs);
+    long long off = 0;
+    for (int b = 0; b < n_bufs; ++b) {
+        p->buf_off[b] = off;
+        long long e = buf_elems[b] * (long long)max_batch;
+        off += (e + 63) / 64 * 64;     // 256-byte alignment of every buffer
+    }
+    p->arena_elems = off;
+    p->bn_off.assign(n_ops, -1);
+    p->argmax.assign(n_ops, nullptr);
+    int max_slot = -1;
+    for (int i = 0; i < n_ops; ++i) {
+        const b2s_op& op = ops[i];
+        if (op.in < 0 || op.in >= n_tensors || op.out < 0 || op.out >= n_tensors) {
+            set_error("b2s_plan_create: op %d references an unknown tensor", i);
+            delete p;
+            return -1;
+        }
+        if (op.kind == B2S_OP_BN) {
+            p->bn_off[i] = p->bn_total;
+            p->bn_total += 2LL * tensors[op.in].C;
+            if (op.slot > max_slot) max_slot = op.slot;
+            ++p->n_bn;
+        }
+    }
+    p->bn_rm.assign(max_slot + 1, nullptr);
+    p->bn_rv.assign(max_slot + 1, nullptr);
+    int rc = 0;
+    auto fail = [&](int code) { b2s_plan_destroy(p); return code; };
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("b2s_plan_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(-2);
+    }
+    if ((rc = alloc_order(p, 0)) != 0) return fail(rc);
+    if ((rc = alloc_order(p, 1)) != 0) return fail(rc);
+    const b2s_tensor& L = tensors[logits];
+    p->n_classes = L.C * L.H * L.W;
+    const size_t lab = (size_t)max_batch * p->n_classes;
+    if (cudaMalloc(&p->params, (size_t)(n_params + 4) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->v32, (size_t)(n_params + 4) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->loss, sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&p->labels, (size_t)max_batch * sizeof(long long)) != cudaSuccess ||
+        cudaMalloc(&p->target, lab * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->coef, lab * sizeof(float)) != cudaSuccess) {
+        set_error("b2s_plan_create: out of device memory: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(-2);
+    }
+    cudaMemset(p->v32, 0, (size_t)(n_params + 4) * sizeof(float));
+    p->workspace += 2 * (n_params + 4) * 4 + (long long)lab * 8;
+    for (int i = 0; i < n_ops; ++i) {
+        if (ops[i].kind == B2S_OP_MAXPOOL) {
+            const b2s_tensor& O = tensors[ops[i].out];
+            const size_t n = (size_t)max_batch * O.C * O.H * O.W;
+            if (cudaMalloc(&p->argmax[i], n * sizeof(int32_t)) != cudaSuccess) {
+                set_error("b2s_plan_create: out of device memory (argmax)");
+                return fail(-2);
+            }
+            p->workspace += (long long)n * 4;
+        }
+    }
+    *out = p;
+    return 0;
+}
+
+int b2s_plan_destroy(b2s_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (auto& kv : p->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (int k = 0; k < 3; ++k) {
+        cudaFree(p->fw[k]); cudaFree(p->bw[k]); cudaFree(p->out32[k]);
+        cudaFree(p->fsum[k]); cudaFree(p->bsum[k]);
+    }
+    for (auto a : p->argmax) cudaFree(a);
+    cudaFree(p->params); cudaFree(p->v32); cudaFree(p->loss);
+    cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
+    if (p->pi) b2s_pi_destroy(p->pi);
+    if (p->comm) comm_destroy(p->comm);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->ev_out) cudaEventDestroy(p->ev_out);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return 0;
+}
+
+int b2s_plan_set_stream(b2s_plan* p, void* cuda_stream) {
+    if (!p) return -1;
+    p->caller = (cudaStream_t)cuda_stream;
+    return 0;
+}
+int b2s_plan_set_graphs(b2s_plan* p, int32_t use_graphs) {
+    if (!p) return -1;
+    p->use_graphs = use_graphs != 0;
+    return 0;
+}
+int64_t b2s_plan_workspace_bytes(const b2s_plan* p) { return p ? p->workspace : 0; }
+
+int b2s_plan_set_bn_buffers(b2s_plan* p, int32_t slot, void* rm, void* rv) {
+    if (!p || slot < 0 || slot >= (int)p->bn_rm.size()) {
+        set_error("b2s_plan_set_bn_buffers: bad slot %d", slot);
+        return -1;
+    }
+    if (p->bn_rm[slot] != rm || p->bn_rv[slot] != rv) {
+        // captured order-0 graphs hold the old pointers
+        for (auto it = p->graphs.begin(); it != p->graphs.end();) {
+            if ((it->first >> 32) == 0) {
+                if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+                it = p->graphs.erase(it);
+            } else {
+                ++it;
+            }
+        }
+    }
+    p->bn_rm[slot] = (float*)rm;
+    p->bn_rv[slot] = (float*)rv;
+    return 0;
+}
+
+int b2s_base_pass(b2s_plan* p, const float* d_params, const float* d_x, const void* d_y, const float* d_coef,
+                  int32_t batch, double loss_scale, double* d_grad_out, double* d_loss_out) {
+    if (!p || !d_params || !d_x || !d_y) { set_error("b2s_base_pass: null argument"); return -1; }
+    if (batch <= 0 || batch > p->max_batch) {
+        set_error("b2s_base_pass: batch %d outside (0, %d]", batch, p->max_batch);
+        return -1;
+    }
+    const bool wbce = p->head == B2S_HEAD_WBCE || p->head == B2S_HEAD_SIGMOID_WBCE;
+    if (wbce && !d_coef) { set_error("b2s_base_pass: weighted-BCE head needs d_coef"); return -1; }
+    B2S_TRY(enter(p));
+    cudaStream_t st = p->stream;
+    if (p->loss_scale != loss_scale) {          // baked into captured head kernels
+        for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        p->graphs.clear();
+    }
+    p->batch = batch;
+    p->loss_scale = loss_scale;
+    p->v_is_current = false;
+    B2S_CUDA(cudaMemcpyAsync(p->params, d_params, (size_t)p->P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const b2s_tensor& X = p->tensors[0];     // tensor 0 is the network input by convention
+    B2S_CUDA(cudaMemcpyAsync(p->fw[0] + p->buf_off[X.buf], d_x,
+                             (size_t)batch * p->buf_elems[X.buf] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (wbce) {
+        const size_t nb = (size_t)batch * p->n_classes * sizeof(float);
+        B2S_CUDA(cudaMemcpyAsync(p->target, d_y, nb, cudaMemcpyDeviceToDevice, st));
+        B2S_CUDA(cudaMemcpyAsync(p->coef, d_coef, nb, cudaMemcpyDeviceToDevice, st));
+    } else {
+        B2S_CUDA(cudaMemcpyAsync(p->labels, d_y, (size_t)batch * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+    }
+    B2S_TRY(run_pass(p, 0));
+    if (d_grad_out) B2S_TRY(launch_cast_f32_f64(st, p->out32[0], d_grad_out, p->P, 1.0));
+    if (d_loss_out) B2S_CUDA(cudaMemcpyAsync(d_loss_out, p->loss, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return leave(p);
+}
+
+static int hv_impl(b2s_plan* p, const double* d_v) {
+    if (p->batch <= 0) { set_error("b2s_hv: call b2s_base_pass first"); return -1; }
+    B2S_TRY(launch_cast_f64_f32(p->stream, d_v, p->v32, p->P));
+    B2S_TRY(run_pass(p, 1));
+    p->v_is_current = true;
+    return 0;
+}
+
+int b2s_hv(b2s_plan* p, const double* d_v, double* d_out) {
+    if (!p || !d_v || !d_out) { set_error("b2s_hv: null argument"); return -1; }
+    B2S_TRY(enter(p));
+    B2S_TRY(hv_impl(p, d_v));
+    B2S_TRY(launch_cast_f32_f64(p->stream, p->out32[1], d_out, p->P, 1.0));
+    return leave(p);
+}
+
+int b2s_vghv(b2s_plan* p, const double* d_v, double* d_out) {
+    if (!p || !d_v || !d_out) { set_error("b2s_vghv: null argument"); return -1; }
+    B2S_TRY(enter(p));
+    B2S_TRY(alloc_order(p, 2));
+    B2S_TRY(hv_impl(p, d_v));          // order-1 caches for this v
+    B2S_TRY(run_pass(p, 2));
+    B2S_TRY(launch_cast_f32_f64(p->stream, p->out32[2], d_out, p->P, 1.0));
+    return leave(p);
+}
+
+const float* b2s_grad_f32(const b2s_plan* p) { return p ? p->out32[0] : nullptr; }
+const float* b2s_hv_f32(const b2s_plan* p) { return p ? p->out32[1] : nullptr; }
+
+// ---- iteration state ---------------------------------------------------------------------------
+static int pi_create_impl(int64_t n, int32_t cap, int32_t device, float* external_v32, b2s_pistate** out) {
+    if (n <= 0 || cap <= 0 || !out) { set_error("b2s_pi_create: invalid arguments"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("b2s_pi_create: no CUDA device is available; this library has no CPU fallback");
+        return -7;
+    }
+    B2S_CUDA(cudaSetDevice(device));
+    b2s_pistate* s = new b2s_pistate();
+    s->device = device; s->n = n; s->cap = cap;
+    const size_t vb = (size_t)(n + 4) * sizeof(double);
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) {
+        ok = ok && cudaMalloc(&s->vbuf[i], vb) == cudaSuccess;
+        ok = ok && cudaMalloc(&s->rbuf[i], vb) == cudaSuccess;
+    }
+    if (external_v32) { s->v32 = external_v32; s->own_v32 = false; }
+    else ok = ok && cudaMalloc(&s->v32, (size_t)(n + 4) * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->alpha, (size_t)cap * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->traj, (size_t)cap * 4 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->scratch, (size_t)pi_scratch_doubles() * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d, sizeof(PiDev)) == cudaSuccess;
+    if (!ok) {
+        set_error("b2s_pi_create: out of device memory: %s", cudaGetErrorString(cudaGetLastError()));
+        b2s_pi_destroy(s);
+        return -2;
+    }
+    cudaMemset(s->d, 0, sizeof(PiDev));
+    *out = s;
+    return 0;
+}
+
+int b2s_pi_create(int64_t n, int32_t cap, int32_t device, b2s_pistate** out) {
+    return pi_create_impl(n, cap, device, nullptr, out);
+}
+
+int b2s_pi_destroy(b2s_pistate* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) { cudaFree(s->vbuf[i]); cudaFree(s->rbuf[i]); }
+    if (s->own_v32) cudaFree(s->v32);
+    cudaFree(s->alpha); cudaFree(s->traj); cudaFree(s->scratch); cudaFree(s->d);
+    delete s;
+    return 0;
+}
+
+int b2s_pi_reset(b2s_pistate* s, const double* d_v0, const b2s_power_cfg* cfg, void* stream) {
+    if (!s || !d_v0 || !cfg) { set_error("b2s_pi_reset: null argument"); return -1; }
+    B2S_CUDA(cudaSetDevice(s->device));
+    return pi_reset_impl(s, d_v0, cfg, (cudaStream_t)stream);
+}
+const float* b2s_pi_v32(const b2s_pistate* s) { return s ? s->v32 : nullptr; }
+
+int b2s_pi_step(b2s_pistate* s, const float* d_hv, void* stream) {
+    if (!s || !d_hv) { set_error("b2s_pi_step: null argument"); return -1; }
+    return launch_pi_step((cudaStream_t)stream, s->d, s->n, d_hv);
+}
+
+const double* b2s_pi_residual(b2s_pistate* s, void* stream) {
+    if (!s) return nullptr;
+    PiDev h;
+    if (cudaMemcpyAsync(&h, s->d, sizeof(PiDev), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+        set_error("b2s_pi_residual: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return s->rbuf[h.r_last];
+}
+
+int b2s_pi_precond_update(b2s_pistate* s, const double* d_Tr, void* stream) {
+    if (!s || !d_Tr) { set_error("b2s_pi_precond_update: null argument"); return -1; }
+    return launch_pi_precond_update((cudaStream_t)stream, s->d, s->n, d_Tr);
+}
+
+int b2s_pi_done(b2s_pistate* s, void* stream) {
+    if (!s) return -1;
+    int done = 0;
+    B2S_CUDA(cudaMemcpyAsync(&done, &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    B2S_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return done;
+}
+
+int b2s_pi_result(b2s_pistate* s, b2s_power_result* r, double* h_traj, double* d_v_out, void* stream) {
+    if (!s) { set_error("b2s_pi_result: null argument"); return -1; }
+    return pi_result_impl(s, r, h_traj, d_v_out, (cudaStream_t)stream);
+}
+
+int b2s_power_iterate(b2s_plan* p, double* d_v, const b2s_power_cfg* cfg, b2s_power_result* h_result,
+                      double* h_traj) {
+    if (!p || !d_v || !cfg) { set_error("b2s_power_iterate: null argument"); return -1; }
+    if (p->batch <= 0) { set_error("b2s_power_iterate: call b2s_base_pass first"); return -1; }
+    if (cfg->precond) {
+        set_error("b2s_power_iterate: the preconditioned variant is driven through b2s_pi_step / "
+                  "b2s_pi_precond_update");
+        return -1;
+    }
+    B2S_TRY(enter(p));
+    if (!p->pi || p->pi->cap < cfg->max_iter) {
+        if (p->pi) { b2s_pi_destroy(p->pi); p->pi = nullptr; }
+        const int cap = cfg->max_iter > 1024 ? cfg->max_iter : 1024;
+        B2S_TRY(pi_create_impl(p->P, cap, p->device, p->v32, &p->pi));
+    }
+    b2s_pistate* s = p->pi;
+    cudaStream_t st = p->stream;
+    B2S_TRY(pi_reset_impl(s, d_v, cfg, st));
+    int done = cfg->max_iter <= 0;
+    while (!done) {
+        // the HVP reads p->v32, which pass B of the previous iteration wrote (the state aliases it)
+        B2S_TRY(run_pass(p, 1));
+        B2S_TRY(launch_pi_step(st, s->d, s->n, p->out32[1]));
+        B2S_CUDA(cudaMemcpyAsync(&done, &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B2S_CUDA(cudaStreamSynchronize(st));
+    }
+    p->v_is_current = false;
+    B2S_TRY(pi_result_impl(s, h_result, h_traj, d_v, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return leave(p);
+}
+
+// ---- data parallelism ---------------------------------------------------------------------------
+int b2s_comm_unique_id(void* h_id128) { return comm_unique_id(h_id128); }
+int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world) {
+    if (!p || !h_id128) { set_error("b2s_comm_init: null argument"); return -1; }
+    B2S_CUDA(cudaSetDevice(p->device));
+    if (p->comm) { comm_destroy(p->comm); p->comm = nullptr; }
+    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
+    p->world = world;
+    if (world <= 1) return 0;
+    return comm_init(&p->comm, h_id128, rank, world);
+}
+int b2s_comm_destroy(b2s_plan* p) {
+    if (!p) return 0;
+    if (p->comm) { comm_destroy(p->comm); p->comm = nullptr; }
+    p->world = 1;
+    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
+    return 0;
+}
+
+}  // extern "C"

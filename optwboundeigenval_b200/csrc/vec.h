@@ -1,0 +1,32 @@
+// vec.h -- device-resident state of the spectral-radius iteration (internal).
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+struct PiDev {
+    long long n;
+    double* vbuf[2];        // current / next eigenvector estimate (fp64, as self.v in opt.py:508)
+    double* rbuf[2];        // residual double buffer (r_old of opt.py:463,485)
+    float* v32;             // fp32 rounding of the current vector = input of the next HVP
+    const double* alpha;    // relaxation per iteration (device array) or NULL = 1
+    double* traj;           // [max_iter][4] rows (lam, n, rn, vnn) or NULL
+    double* scratch;        // per-block partial sums
+    unsigned counter;       // last-block detection (self resetting)
+    int cur, rcur, has_old, r_last;
+    int precond;            // 1: K-FAC preconditioned update, finished by launch_pi_precond_update
+    int pending;
+    int iter, max_iter, last_iter;
+    int done, converged;
+    double eps;
+    double sign, lam, vnn, cur_alpha, inv_norm;
+    double norm, rn, n_old, lam_old;
+    double stop[3];
+};
+
+int pi_scratch_doubles();
+// one iteration's vector work: pass A (dots) + pass B (residual, stopping test, update)
+int launch_pi_step(cudaStream_t st, PiDev* dS, long long n, const float* hv);
+int launch_pi_precond_update(cudaStream_t st, PiDev* dS, long long n, const double* Tr);
+
+}  // namespace b2s

@@ -1,0 +1,175 @@
+"""The jet recurrences over the traced tape (what the CUDA library implements) must agree with
+nested autograd (what the reference does, pinned by golden vectors).  CPU only, fp64."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from optwboundeigenval_b200 import tracer, zoo
+from optwboundeigenval_b200.hvp_operator import SpectralPlan
+from oracle import autograd_oracle as ao
+from oracle.jet_oracle import JetTapeOracle
+
+CASES = [("forest", 16), ("usps", 8), ("cifar_densenet", 4)]
+
+
+def _setup(kind, batch, dtype=torch.float64):
+    model, loss = zoo.build(kind)
+    model.train()
+    if kind == "cifar_densenet":      # make BN affine parameters non-trivial
+        g = torch.Generator().manual_seed(5)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.data = 1 + 0.3 * torch.randn(m.weight.shape, generator=g)
+                m.bias.data = 0.2 * torch.randn(m.bias.shape, generator=g)
+    x, y = zoo.synthetic_batch(kind, batch)
+    return model, loss, x, y
+
+
+def _fd_second(model, loss, x, y, v, h=1e-3):
+    """central second difference of the gradient along v: d^2/dt^2 grad E(w + t v)"""
+    w0 = ao.flat_params(model).clone()
+
+    def grad_at(t):
+        off = 0
+        for p in model.parameters():
+            k = p.numel()
+            p.data = (w0 + t * v)[off:off + k].view(p.shape).clone()
+            off += k
+        out = torch.autograd.grad(loss(model(x), y), list(model.parameters()))
+        return torch.cat([g.reshape(-1) for g in out])
+
+    fd = (grad_at(h) - 2 * grad_at(0.0) + grad_at(-h)) / h ** 2
+    grad_at(0.0)
+    return fd
+
+
+@pytest.mark.parametrize("kind,batch", CASES)
+def test_jets_match_autograd_fp64(kind, batch):
+    model, loss, x, y = _setup(kind, batch)
+    tape = tracer.trace(model, loss, zoo.CONFIGS[kind][1])
+    model64 = model.double()
+    op = ao.AutogradSpectralOperator(model64, [x.double(), y], loss)
+    P = tape.n_params
+    g = torch.Generator().manual_seed(11)
+    v = torch.randn(P, generator=g, dtype=torch.float64)
+    v /= v.norm()
+    v = v.float().double()          # fp32-representable so both sides see the same vector
+    jo = JetTapeOracle(tape, ao.flat_params(model64), x, y)
+    g0 = jo.run(0).clone()
+    assert rel_err(g0.numpy(), op.gradient().detach().numpy()) < 1e-10
+    assert abs(float(jo.loss) - op.loss_value) < 1e-10
+    hv = jo.run(1, v).clone()
+    assert rel_err(hv.numpy(), op.hv(v).numpy()) < 1e-9
+    vghv = jo.vghv(v, mode="reference")
+    assert rel_err(vghv.numpy(), op.vghv(v).numpy()) < 1e-8
+    if kind == "cifar_densenet":
+        # torch's third order through native batch norm is NOT the true derivative
+        assert rel_err(jo.vghv(v, mode="exact").numpy(), op.vghv(v).numpy()) > 1e-3
+
+
+@pytest.mark.parametrize("kind", ["chest_vgg_tiny", "chest_densenet_tiny"])
+def test_jets_match_autograd_weighted_bce(kind):
+    """Both chest heads (raw logits, and sigmoid in front of BCE-with-logits) on a small stand-in network
+    with the same layer kinds (conv+bias, BN, ReLU, max pool with padding, concatenation)."""
+    torch.manual_seed(3)
+    nn = torch.nn
+
+    class TinyVgg(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.Sequential(nn.Conv2d(3, 6, 3, padding=1), nn.BatchNorm2d(6), nn.ReLU(inplace=True),
+                                          nn.MaxPool2d(2, 2), nn.Conv2d(6, 8, 3, padding=1), nn.BatchNorm2d(8),
+                                          nn.ReLU(inplace=True), nn.MaxPool2d(2, padding=1), nn.MaxPool2d(3))
+            self.classifier = nn.Linear(8, 5)
+
+        def forward(self, x):
+            return self.classifier(self.features(x).view(-1, 8))
+
+    class TinyDense(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv0 = nn.Conv2d(3, 4, 7, stride=2, padding=3, bias=False)
+            self.norm0 = nn.BatchNorm2d(4)
+            self.pool0 = nn.MaxPool2d(3, stride=2, padding=1)
+            self.n1, self.c1 = nn.BatchNorm2d(4), nn.Conv2d(4, 3, 1, bias=False)
+            self.n2, self.c2 = nn.BatchNorm2d(7), nn.Conv2d(7, 3, 3, padding=1, bias=False)
+            self.tn, self.tc, self.tp = nn.BatchNorm2d(10), nn.Conv2d(10, 5, 1, bias=False), nn.AvgPool2d(2, 2)
+            self.norm5 = nn.BatchNorm2d(5)
+            self.classifier = nn.Sequential(nn.Linear(5, 5), nn.Sigmoid())
+
+        def forward(self, x):
+            f0 = self.pool0(torch.relu(self.norm0(self.conv0(x))))
+            feats = [f0]
+            feats.append(self.c1(torch.relu(self.n1(torch.cat(feats, 1)))))
+            feats.append(self.c2(torch.relu(self.n2(torch.cat(feats, 1)))))
+            h = self.tp(self.tc(torch.relu(self.tn(torch.cat(feats, 1)))))
+            h = torch.nn.functional.relu(self.norm5(h), inplace=True)
+            h = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(h, (1, 1)), 1)
+            return self.classifier(h)
+
+    model = (TinyVgg() if kind == "chest_vgg_tiny" else TinyDense()).double().train()
+    loss = zoo.WeightedBCEWithLogits()
+    B = 6
+    x = torch.randn(B, 3, 16, 16, dtype=torch.float64)
+    y = (torch.rand(B, 5) > 0.7).double()
+    y[0, 1] = float("nan")           # masked label
+    tape = tracer.trace(model, loss, (3, 16, 16))
+    assert not any(o.kind == tracer.OP_COPY for o in tape.ops)
+    op = ao.AutogradSpectralOperator(model, [x, y], loss)
+    t, coef = SpectralPlan.wbce_coefficients(y.float())
+    jo = JetTapeOracle(tape, ao.flat_params(model), x, t, coef, loss_scale=1.0)
+    P = tape.n_params
+    v = torch.randn(P, dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 1e-6     # coef is fp32
+    assert abs(float(jo.loss) - op.loss_value) < 1e-6
+    assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 1e-6
+    assert rel_err(jo.vghv(v, mode="reference").numpy(), op.vghv(v).numpy()) < 1e-6
+
+
+def test_full_size_chest_models_trace():
+    for kind in ("chest_vgg", "chest_densenet121"):
+        model, loss = zoo.build(kind)
+        tape = tracer.trace(model, loss, zoo.CONFIGS[kind][1])
+        assert tape.n_params == sum(p.numel() for p in model.parameters())
+        assert not any(o.kind == tracer.OP_COPY for o in tape.ops)     # all concatenations alias
+        assert not any(o.kind == tracer.OP_RELU for o in tape.ops)     # all ReLUs fused
+
+
+def test_exact_third_order_is_the_true_derivative_and_torch_bn_is_not():
+    """On a smooth network (no ReLU) with train-mode BatchNorm, d^2/dt^2 grad E(w+tv) by central
+    differences agrees with the exact jets, while nested autograd through native_batch_norm does not:
+    batchnorm_double_backward reads mean / invstd from saved non-differentiable tensors."""
+    torch.manual_seed(0)
+    nn = torch.nn
+
+    class Smooth(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(2, 3, 3, padding=1, bias=False)
+            self.b = nn.BatchNorm2d(3)
+            self.f = nn.Linear(48, 4)
+
+        def forward(self, x):
+            return self.f(self.b(self.c(x)).view(-1, 48))
+
+    model = Smooth().double().train()
+    model.b.weight.data = 1 + 0.3 * torch.randn(3, dtype=torch.float64)
+    model.b.bias.data = 0.2 * torch.randn(3, dtype=torch.float64)
+    x = torch.randn(5, 2, 4, 4, dtype=torch.float64)
+    y = torch.randint(0, 4, (5,))
+    loss = nn.CrossEntropyLoss()
+    tape = tracer.trace(model, loss, (2, 4, 4))
+    v = torch.randn(tape.n_params, dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    op = ao.AutogradSpectralOperator(model, [x, y], loss)
+    ref = op.vghv(v)
+    jo = JetTapeOracle(tape, ao.flat_params(model), x, y)
+    jo.run(0)
+    exact = jo.vghv(v, mode="exact")
+    compat = jo.vghv(v, mode="reference")
+    fd = _fd_second(model, loss, x, y, v)
+    assert rel_err(exact.numpy(), fd.numpy()) < 1e-5
+    assert rel_err(compat.numpy(), ref.numpy()) < 1e-10
+    assert rel_err(ref.numpy(), fd.numpy()) > 1e-2
