@@ -103,6 +103,13 @@ int b2s_plan_set_stream(b2s_plan* p, void* cuda_stream);
 /* use_graphs != 0: each pass is captured once per batch size into a CUDA graph and replayed */
 int b2s_plan_set_graphs(b2s_plan* p, int32_t use_graphs);
 int64_t b2s_plan_workspace_bytes(const b2s_plan* p);
+/* Third-order derivative through train-mode BatchNorm used by b2s_vghv.
+ * exact = 0 (default): reproduce what nested torch.autograd returns for HVPOperator.vGHv
+ *   (opt.py:132-143).  torch's batchnorm_double_backward reads the batch mean / inverse std from
+ *   saved non-differentiable tensors, so its third sweep drops every path through them; the library
+ *   computes the exact result and subtracts exactly those dropped terms (DESIGN.md "BatchNorm").
+ * exact = 1: the true gradient of v^T H v (agrees with finite differences of the gradient). */
+int b2s_plan_set_bn_third_order(b2s_plan* p, int32_t exact);
 /* device pointers (float*) of the running_mean / running_var tensors of BN slot `slot`
  * (updated in place by the base pass exactly like a train-mode forward, opt.py:181,421) */
 int b2s_plan_set_bn_buffers(b2s_plan* p, int32_t slot, void* d_running_mean, void* d_running_var);
@@ -125,6 +132,10 @@ int b2s_vghv(b2s_plan* p, const double* d_v, double* d_out);
 /* fp32 results of the last passes, device pointers owned by the plan (float [n_params]) */
 const float* b2s_grad_f32(const b2s_plan* p);
 const float* b2s_hv_f32(const b2s_plan* p);
+
+/* test hook: copies one cached tensor (adjoint = 0: value jets, 1: adjoint jets; order 0..2) of the
+ * last passes to host memory, densely packed [batch, C, H, W]. Synchronises. */
+int b2s_debug_read(b2s_plan* p, int32_t adjoint, int32_t order, int32_t tensor, float* h_out);
 
 /* ---- spectral-radius iteration ------------------------------------------------------- */
 typedef struct {

@@ -36,11 +36,13 @@ SIGNATURES = {
     "b2s_plan_set_stream": (c_int32, [c_void_p, c_void_p]),
     "b2s_plan_set_graphs": (c_int32, [c_void_p, c_int32]),
     "b2s_plan_workspace_bytes": (c_int64, [c_void_p]),
+    "b2s_plan_set_bn_third_order": (c_int32, [c_void_p, c_int32]),
     "b2s_plan_set_bn_buffers": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
     "b2s_base_pass": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_void_p,
                                 c_void_p]),
     "b2s_hv": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_vghv": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "b2s_debug_read": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b2s_grad_f32": (c_void_p, [c_void_p]),
     "b2s_hv_f32": (c_void_p, [c_void_p]),
     "b2s_power_iterate": (c_int32, [c_void_p, c_void_p, POINTER(PowerCfg), POINTER(PowerResult), c_void_p]),

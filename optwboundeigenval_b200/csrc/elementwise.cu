@@ -168,6 +168,13 @@ __global__ void cast_f32_f64_kernel(const float* __restrict__ in, double* __rest
         out[i] = (double)in[i] * scale;
 }
 
+__global__ void sub_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ out,
+                                long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = (double)(a[i] - b[i]);
+}
+
 static inline long long per_sample(const View& v) { return (long long)v.C * v.H * v.W; }
 
 int launch_relu_fwd(cudaStream_t st, int order, const View& x0, const View& xk, const View& yk, int batch) {
@@ -252,6 +259,15 @@ int launch_cast_f32_f64(cudaStream_t st, const float* in, double* out, long long
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     if (blocks < 1) blocks = 1;
     cast_f32_f64_kernel<<<blocks, 256, 0, st>>>(in, out, n, scale);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_sub_cast_f32_f64(cudaStream_t st, const float* a, const float* b, double* out, long long n) {
+    int blocks = cdiv(n, 256 * 4);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    sub_cast_kernel<<<blocks, 256, 0, st>>>(a, b, out, n);
     B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -78,11 +78,17 @@ struct BnArgs {
     long long count;          // elements per channel over the GLOBAL batch (batch*HW on one GPU)
     int accumulate;
     float pgrad_scale;        // 1/world when the sums were all-reduced (the flat vector is summed again later)
+    double* csum;             // third-order compatibility sweep: [bn_corr_sums()][C]
 };
 int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_bwd_apply(cudaStream_t st, int order, const BnArgs& a);
+// reference-compatible third order (see bn.cu): first-order sweep with the dropped adjoint injected
+int bn_corr_sums();
+int launch_bn_corr_stats(cudaStream_t st, const BnArgs& a, const float* gc);
+int launch_bn_corr_apply(cudaStream_t st, const BnArgs& a, const float* gc, float* xbar);
+int launch_sub_cast_f32_f64(cudaStream_t st, const float* a, const float* b, double* out, long long n);
 
 // ---- loss heads (head.cu) -------------------------------------------------------------
 struct HeadArgs {

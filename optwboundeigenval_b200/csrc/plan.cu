@@ -101,6 +101,9 @@ struct b2s_plan {
     long long bn_total = 0;
     double* fsum[3] = {nullptr, nullptr, nullptr};
     double* bsum[3] = {nullptr, nullptr, nullptr};
+    double* csum = nullptr;           // sums of the third-order compatibility sweep
+    float* out_corr = nullptr;        // its parameter-space result
+    bool bn_exact_third_order = false;
     std::vector<float*> bn_rm, bn_rv;
 
     // max pool
@@ -354,7 +357,77 @@ static int backward(b2s_plan* p, int K) {
     return 0;
 }
 
+// First-order backward sweep with zero loss seed that carries the adjoint torch's third-order
+// BatchNorm derivative drops (bn.cu, "reference-compatible third order").  Runs after pass 2 and
+// reuses its adjoint arena bw[2]; result in p->out_corr.
+static int backward_correction(b2s_plan* p) {
+    cudaStream_t st = p->stream;
+    const int ns = bn_corr_sums();
+    B2S_CUDA(cudaMemsetAsync(p->out_corr, 0, (size_t)p->P * sizeof(float), st));
+    B2S_CUDA(cudaMemsetAsync(p->csum, 0, (size_t)p->bn_total / 2 * ns * sizeof(double), st));
+    B2S_TRY(launch_zero_view(st, tview(p, p->bw, 2, p->logits), p->batch));
+    for (int oi = (int)p->ops.size() - 1; oi >= 0; --oi) {
+        const b2s_op& op = p->ops[oi];
+        const bool first = op.flags & B2S_F_FIRST;
+        const bool relu = op.flags & B2S_F_RELU;
+        const int acc = (op.flags & B2S_F_BWD_ACC) ? 1 : 0;
+        switch (op.kind) {
+        case B2S_OP_CONV: {
+            const ConvGeom g = conv_geom(p, op);
+            if (relu) B2S_TRY(launch_mask_inplace(st, tview(p, p->fw, 0, op.out), tview(p, p->bw, 2, op.out), p->batch));
+            const float* x0 = tptr(p, p->fw, 0, op.in);
+            const float* gc = tptr(p, p->bw, 2, op.out);
+            const float* W = p->params + op.w_off;
+            const float one = 1.f;
+            B2S_TRY(launch_conv_wgrad(st, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
+            if (op.b_off >= 0)
+                B2S_TRY(launch_bias_grad(st, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
+            if (!first) B2S_TRY(launch_conv_dgrad(st, g, 1, &gc, &W, &one, tptr(p, p->bw, 2, op.in), acc));
+            break;
+        }
+        case B2S_OP_BN: {
+            BnArgs a = bn_args(p, oi, 1);
+            a.csum = p->csum + p->bn_off[oi] / 2 * ns;
+            a.out_gamma = p->out_corr + op.w_off;
+            a.out_beta = p->out_corr + op.b_off;
+            const float* gc = tptr(p, p->bw, 2, op.out);
+            B2S_TRY(launch_bn_corr_stats(st, a, gc));
+            if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.csum, ns * a.C, st));
+            B2S_TRY(launch_bn_corr_apply(st, a, gc, first ? nullptr : tptr(p, p->bw, 2, op.in)));
+            break;
+        }
+        case B2S_OP_RELU:
+            if (!first)
+                B2S_TRY(launch_relu_bwd(st, tview(p, p->fw, 0, op.in), tview(p, p->bw, 2, op.out),
+                                        tview(p, p->bw, 2, op.in), p->batch, acc));
+            break;
+        case B2S_OP_MAXPOOL:
+            if (!first) {
+                if (!acc) B2S_TRY(launch_zero_view(st, tview(p, p->bw, 2, op.in), p->batch));
+                B2S_TRY(launch_maxpool_bwd(st, tview(p, p->bw, 2, op.out), tview(p, p->bw, 2, op.in),
+                                           p->argmax[oi], p->batch));
+            }
+            break;
+        case B2S_OP_AVGPOOL:
+            if (!first)
+                B2S_TRY(launch_avgpool_bwd(st, tview(p, p->bw, 2, op.out), tview(p, p->bw, 2, op.in), p->batch,
+                                           op.kh, acc));
+            break;
+        case B2S_OP_COPY:
+            if (!first)
+                B2S_TRY(launch_copy_view(st, tview(p, p->bw, 2, op.out), tview(p, p->bw, 2, op.in), p->batch, acc));
+            break;
+        default:
+            set_error("unknown op kind %d", op.kind);
+            return -5;
+        }
+    }
+    if (p->comm) B2S_TRY(comm_allreduce_f32(p->comm, p->out_corr, p->P, st));
+    return 0;
+}
+
 static int run_pass_eager(b2s_plan* p, int K) {
+    if (K == 3) return backward_correction(p);
     B2S_TRY(forward(p, K));
     B2S_TRY(backward(p, K));
     return 0;
@@ -362,7 +435,7 @@ static int run_pass_eager(b2s_plan* p, int K) {
 
 // one pass of order K on p->stream, through a CUDA graph when enabled
 static int run_pass(b2s_plan* p, int K) {
-    B2S_TRY(alloc_order(p, K));
+    if (K < 3) B2S_TRY(alloc_order(p, K));
     if (!p->use_graphs) return run_pass_eager(p, K);
     const long long key = ((long long)K << 32) | (unsigned)p->batch;
     auto it = p->graphs.find(key);
@@ -595,6 +668,7 @@ int b2s_plan_destroy(b2s_plan* p) {
         cudaFree(p->fsum[k]); cudaFree(p->bsum[k]);
     }
     for (auto a : p->argmax) cudaFree(a);
+    cudaFree(p->csum); cudaFree(p->out_corr);
     cudaFree(p->params); cudaFree(p->v32); cudaFree(p->loss);
     cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
     if (p->pi) b2s_pi_destroy(p->pi);
@@ -617,6 +691,11 @@ int b2s_plan_set_graphs(b2s_plan* p, int32_t use_graphs) {
     return 0;
 }
 int64_t b2s_plan_workspace_bytes(const b2s_plan* p) { return p ? p->workspace : 0; }
+int b2s_plan_set_bn_third_order(b2s_plan* p, int32_t exact) {
+    if (!p) return -1;
+    p->bn_exact_third_order = exact != 0;
+    return 0;
+}
 
 int b2s_plan_set_bn_buffers(b2s_plan* p, int32_t slot, void* rm, void* rv) {
     if (!p || slot < 0 || slot >= (int)p->bn_rm.size()) {
@@ -696,8 +775,33 @@ int b2s_vghv(b2s_plan* p, const double* d_v, double* d_out) {
     B2S_TRY(alloc_order(p, 2));
     B2S_TRY(hv_impl(p, d_v));          // order-1 caches for this v
     B2S_TRY(run_pass(p, 2));
-    B2S_TRY(launch_cast_f32_f64(p->stream, p->out32[2], d_out, p->P, 1.0));
+    if (p->n_bn > 0 && !p->bn_exact_third_order) {
+        if (!p->out_corr) {
+            B2S_CUDA(cudaMalloc(&p->out_corr, (size_t)(p->P + 4) * sizeof(float)));
+            B2S_CUDA(cudaMalloc(&p->csum, (size_t)p->bn_total / 2 * bn_corr_sums() * sizeof(double)));
+        }
+        B2S_TRY(run_pass(p, 3));
+        B2S_TRY(launch_sub_cast_f32_f64(p->stream, p->out32[2], p->out_corr, d_out, p->P));
+    } else {
+        B2S_TRY(launch_cast_f32_f64(p->stream, p->out32[2], d_out, p->P, 1.0));
+    }
     return leave(p);
+}
+
+int b2s_debug_read(b2s_plan* p, int32_t adjoint, int32_t order, int32_t tensor, float* h_out) {
+    if (!p || !h_out || order < 0 || order > 2 || tensor < 0 || tensor >= (int)p->tensors.size()) {
+        set_error("b2s_debug_read: invalid arguments");
+        return -1;
+    }
+    float* const* arena = adjoint ? p->bw : p->fw;
+    if (!arena[order] || p->batch <= 0) { set_error("b2s_debug_read: nothing cached for that order"); return -1; }
+    B2S_CUDA(cudaSetDevice(p->device));
+    B2S_CUDA(cudaStreamSynchronize(p->stream));
+    const b2s_tensor& T = p->tensors[tensor];
+    const size_t n = (size_t)T.C * T.H * T.W;
+    B2S_CUDA(cudaMemcpy2D(h_out, n * sizeof(float), tptr(p, arena, order, tensor), (size_t)T.sample_stride * sizeof(float),
+                          n * sizeof(float), (size_t)p->batch, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 const float* b2s_grad_f32(const b2s_plan* p) { return p ? p->out32[0] : nullptr; }
