@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- HVPs/sec of the spectral-radius hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): params/cifar10_DenseNet_mu0_01_K10.py -- DenseNet3(40,12) on synthetic
+32x32 images, 32 images per GPU (the reference's batch size), power iteration for lambda_max.
+A *step* is one iteration of comp_rho's loop (opt.py:447-498) in steady state: one Hessian-vector
+product of the cached minibatch (HVPOperator.Hv(v, storedGrad=True), opt.py:77-108) plus the
+vector algebra and stopping test; the base pass (prepare_grad) is cached exactly as in the reference.
+
+value   device-resident throughput: b2s_power_iterate run for exactly K iterations (eps = 0).
+        With N GPUs each rank holds its own 32-image shard (weak scaling, global batch 32 N, synced
+        BatchNorm statistics, one NCCL all-reduce of the P-vector per HVP); value counts
+        32-image-minibatch HVP equivalents: N * K / time.
+e2e     the same HVP through the reference-facing call B200HVPOperator.Hv(vec) with a HOST vector:
+        per step 8P bytes host->device (pinned) and 8P bytes device->host are inside the timed region.
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+--impl reference times the CPU restatement of the reference's algorithm (oracle/, nested torch.autograd
+on all host cores) on the same config; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi SM clocks / throttle reasons while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        import statistics
+        mhz = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(mhz) if mhz else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_hvp_rate(kind, batch, seconds_budget=20.0, min_calls=3):
+    """HVPs/sec of the oracle port (the reference's nested-autograd algorithm) on all host cores."""
+    import torch
+    from optwboundeigenval_b200 import zoo
+    from oracle import autograd_oracle as ao
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, loss = zoo.build(kind)
+    model.train()
+    x, y = zoo.synthetic_batch(kind, batch)
+    op = ao.AutogradSpectralOperator(model, [x, y], loss)
+    P = sum(p.numel() for p in model.parameters())
+    v = ao.start_vector(P)
+    op.hv(v)                      # builds the graph (prepare_grad) + first double backward: warm-up
+    op.hv(v)
+    t0 = time.time()
+    n = 0
+    while n < min_calls or (time.time() - t0 < seconds_budget and n < 200):
+        op.hv(v)
+        n += 1
+    dt = time.time() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from optwboundeigenval_b200 import zoo
+    from oracle import autograd_oracle as ao
+    kind, batch = args.config, args.batch or zoo.CONFIGS[args.config][3]
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, loss = zoo.build(kind)
+    model.train()
+    x, y = zoo.synthetic_batch(kind, batch)
+    op = ao.AutogradSpectralOperator(model, [x, y], loss)
+    P = sum(p.numel() for p in model.parameters())
+    v = ao.start_vector(P)
+    for _ in range(max(args.warmup, 1)):
+        op.hv(v)
+    t0 = time.time()
+    for _ in range(args.steps):
+        w = op.hv(v)
+        lam = float(torch.dot(w, v))
+        v = w / torch.norm(w) if lam >= 0 else -w / torch.norm(w)
+    dt = time.time() - t0
+    val = args.steps / dt
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": "HVPs/sec (power-iter lambda_max)", "value": val, "unit": "HVP/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(kind, batch, 1),
+            "cpu_baseline": {"value": val, "unit": "HVP/s", "cores": cores, "kind": "port",
+                             "sample": "%d power-iteration HVPs of one %d-image minibatch (oracle/autograd_oracle.py, "
+                                       "nested torch.autograd on CPU, torch threads = %d)" % (args.steps, batch, cores)},
+            "e2e": {"value": val, "unit": "HVP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _config(kind, batch, world):
+    names = {"cifar_densenet": "params/cifar10_DenseNet_mu0_01_K10.py: DenseNet3(40,12), 32x32 synthetic images",
+             "usps": "params/usps_CNN_mu0_01_K0.py: USPS CNN, 16x16 synthetic digits",
+             "forest": "params/forest_best.py: covertype MLP 54-20-20-20-7",
+             "chest_vgg": "params/chestxray_mu0_001_K0_vgg.py: VGG16-bn chest model, 224x224 synthetic",
+             "chest_densenet121": "params/chestxray_best_reg.py: DenseNet121 chest model, 224x224 synthetic"}
+    return {"workload": names[kind], "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": "dp%d (minibatch sharded, synced BatchNorm sums, one NCCL all-reduce of the P-vector per HVP)" % world
+            if world > 1 else "single GPU",
+            "l2": "no flush: the HVP streams its value/tangent/adjoint caches, working set far above the 126 MB L2"}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from optwboundeigenval_b200 import _lib, zoo
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kind = args.config
+    batch = args.batch or zoo.CONFIGS[kind][3]
+    model, loss = zoo.build(kind)            # same seed on every rank: replicated parameters
+    model.train()
+    x, y = zoo.synthetic_batch(kind, batch, seed=zoo.SEED + 1000 * rank)     # each rank its own shard
+    op = B200HVPOperator(model, [x, y], loss)
+    P = sum(p.numel() for p in model.parameters())
+    v0 = torch.from_numpy(np.ones(P) / np.sqrt(P)).cuda()
+    op.Hv(v0, storedGrad=True)               # base pass + first HVP: plan, workspaces, graph capture
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop -------------------------------------------------------------------
+    op.power_iterate(v0, 0.0, max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    out = op.power_iterate(v0, 0.0, args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert out.iters == args.steps - 1, "the timed loop must run exactly --steps iterations"
+
+    # ---- end to end through the reference-facing operator call, host vectors ----------------------
+    v_host = torch.from_numpy(np.ones(P) / np.sqrt(P)).pin_memory()
+    for _ in range(3):
+        op.Hv(v_host, storedGrad=True).cpu()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        r = op.Hv(v_host, storedGrad=True).cpu()
+        v_host.copy_(r / torch.norm(r))
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel family of the HVP pass (events around every launch) -------
+    peaks = _peaks()
+    prof = op.plan.profile(1, reps=3) if rank == 0 else []
+    line = None
+    if rank == 0:
+        top = max(prof, key=lambda r: r["ms"])
+        tot_ms = sum(r["ms"] for r in prof)
+        is_gemm = top["name"].startswith("conv")
+        if is_gemm:
+            achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops"], "traffic": None}
+        else:
+            achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+        roof.update({"kernel": top["name"], "launches_per_step": top["launches"],
+                     "ms_per_step_in_kernel": top["ms"], "share_of_step_kernel_time": top["ms"] / tot_ms,
+                     "peak_source": peaks["source"] + (" bf16 burst" if is_gemm else " copy"),
+                     "note": "fp32-exact CUDA-core contraction measured against the bf16 tensor peak"
+                     if is_gemm else "algorithmic bytes / CUDA-event time"})
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            rate, n, dt = cpu_hvp_rate(kind, batch)
+            cpu = {"value": rate, "unit": "HVP/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "%d Hv calls of the same %d-image minibatch in %.1f s (oracle/autograd_oracle.py)" % (n, batch, dt)}
+        value = world * args.steps / (ms * 1e-3)
+        line = {"metric": "HVPs/sec (power-iter lambda_max)", "value": value,
+                "unit": "HVP/s (32-image minibatch equivalents)" if kind == "cifar_densenet" else "HVP/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": _config(kind, batch, world),
+                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "HVP/s",
+                        "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * P},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "roofline": roof,
+                "cpu_baseline": cpu,
+                "kernel_profile_ms": {r["name"]: round(r["ms"], 4) for r in prof},
+                "lambda_max": out.lam}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cifar_densenet")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 12)
+        args.warmup = min(args.warmup, 2)
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

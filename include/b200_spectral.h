@@ -137,6 +137,19 @@ const float* b2s_hv_f32(const b2s_plan* p);
  * last passes to host memory, densely packed [batch, C, H, W]. Synchronises. */
 int b2s_debug_read(b2s_plan* p, int32_t adjoint, int32_t order, int32_t tensor, float* h_out);
 
+/* Built-in per-launch timer: runs pass `order` (0 base, 1 Hv, 2 second order, 3 BatchNorm
+ * compatibility sweep) eagerly `reps` times with a CUDA-event pair around every kernel on the
+ * launching stream and returns, per kernel family, launches / device milliseconds / algorithmic
+ * FLOPs and bytes PER PASS.  bench.py derives the roofline line from this. Synchronises. */
+typedef struct {
+    char name[48];
+    int32_t launches;
+    double ms;
+    double flops;
+    double bytes;
+} b2s_prof_entry;
+int b2s_profile_pass(b2s_plan* p, int32_t order, int32_t reps, b2s_prof_entry* out, int32_t cap, int32_t* n_out);
+
 /* ---- spectral-radius iteration ------------------------------------------------------- */
 typedef struct {
     int32_t max_iter;        /* min(ndim, max_pow_iter)                                     opt.py:447 */

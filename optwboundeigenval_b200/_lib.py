@@ -25,6 +25,11 @@ class PowerResult(ctypes.Structure):
                 ("rn", c_double), ("vnn", c_double), ("stop", c_double * 3)]
 
 
+class ProfEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("launches", c_int32), ("ms", c_double), ("flops", c_double),
+                ("bytes", c_double)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "b2s_abi_version": (c_int32, []),
@@ -43,6 +48,7 @@ SIGNATURES = {
     "b2s_hv": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_vghv": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_debug_read": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "b2s_profile_pass": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ProfEntry), c_int32, POINTER(c_int32)]),
     "b2s_grad_f32": (c_void_p, [c_void_p]),
     "b2s_hv_f32": (c_void_p, [c_void_p]),
     "b2s_power_iterate": (c_int32, [c_void_p, c_void_p, POINTER(PowerCfg), POINTER(PowerResult), c_void_p]),

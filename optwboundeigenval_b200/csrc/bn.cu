@@ -237,6 +237,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float
 
 int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a) {
     const dim3 grid = bn_grid(a);
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_fwd_stats", 8.0 * elems, 4.0 * elems * (order + 1), st);
     if (order == 0) bn_fwd_stats_kernel<0><<<grid, 256, 0, st>>>(a);
     else if (order == 1) bn_fwd_stats_kernel<1><<<grid, 256, 0, st>>>(a);
     else bn_fwd_stats_kernel<2><<<grid, 256, 0, st>>>(a);
@@ -245,6 +247,8 @@ int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a) {
 }
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a) {
     const dim3 grid = bn_grid(a);
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_fwd_apply", 8.0 * elems, 4.0 * elems * (order + 2), st);
     if (order == 0) bn_fwd_apply_kernel<0><<<grid, 256, 0, st>>>(a);
     else if (order == 1) bn_fwd_apply_kernel<1><<<grid, 256, 0, st>>>(a);
     else bn_fwd_apply_kernel<2><<<grid, 256, 0, st>>>(a);
@@ -253,6 +257,8 @@ int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a) {
 }
 int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a) {
     const dim3 grid = bn_grid(a);
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_bwd_stats", 8.0 * elems, 4.0 * elems * (2 * order + 3), st);
     if (order == 0) bn_bwd_stats_kernel<0><<<grid, 256, 0, st>>>(a);
     else if (order == 1) bn_bwd_stats_kernel<1><<<grid, 256, 0, st>>>(a);
     else bn_bwd_stats_kernel<2><<<grid, 256, 0, st>>>(a);
@@ -261,6 +267,8 @@ int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a) {
 }
 int launch_bn_bwd_apply(cudaStream_t st, int order, const BnArgs& a) {
     const dim3 grid = bn_grid(a);
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_bwd_apply", 8.0 * elems, 4.0 * elems * (2 * order + 4), st);
     const float ps = a.pgrad_scale;
     if (order == 0) bn_bwd_apply_kernel<0><<<grid, 256, 0, st>>>(a, ps);
     else if (order == 1) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(a, ps);
@@ -367,11 +375,13 @@ __global__ void __launch_bounds__(256) bn_corr_apply_kernel(const BnArgs a, cons
 int bn_corr_sums() { return kCorrSums; }
 
 int launch_bn_corr_stats(cudaStream_t st, const BnArgs& a, const float* gc) {
+    ProfScope prof("bn_corr_stats", 20.0 * a.batch * a.C * a.HW, 4.0 * 6 * (double)a.batch * a.C * a.HW, st);
     bn_corr_stats_kernel<<<bn_grid(a), 256, 0, st>>>(a, gc);
     B2S_LAUNCH_CHECK();
     return 0;
 }
 int launch_bn_corr_apply(cudaStream_t st, const BnArgs& a, const float* gc, float* xbar) {
+    ProfScope prof("bn_corr_apply", 8.0 * a.batch * a.C * a.HW, 4.0 * 4 * (double)a.batch * a.C * a.HW, st);
     bn_corr_apply_kernel<<<bn_grid(a), 256, 0, st>>>(a, gc, xbar, a.pgrad_scale);
     B2S_LAUNCH_CHECK();
     return 0;

@@ -38,6 +38,16 @@ void count_launch(int n = 1);
         if (rc_ != 0) return rc_;                                                          \
     } while (0)
 
+// ---- built-in per-launch timer (used by b2s_profile_pass for the roofline numbers) -----------
+// When a profiler is active on this thread, every launcher brackets its kernel with CUDA events on
+// the launching stream and tags it with its algorithmic FLOPs and bytes.
+struct ProfScope {
+    int idx;
+    cudaStream_t st;
+    ProfScope(const char* name, double flops, double bytes, cudaStream_t stream);
+    ~ProfScope();
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs

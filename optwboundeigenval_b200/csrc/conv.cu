@@ -322,6 +322,10 @@ static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
     const ConvGeom& g = a.g;
     const int Cd = MODE == MODE_FWD ? g.Cout : g.Cin;
     const long long J = (long long)g.batch * (MODE == MODE_FWD ? g.OH * g.OW : g.H * g.W);
+    const double macs = (double)g.batch * g.OH * g.OW * g.Cout * g.Cin * g.KH * g.KW;      // per pair
+    const double io = 4.0 * ((double)g.batch * g.Cin * g.H * g.W * a.npairs + (double)g.batch * g.Cout * g.OH * g.OW +
+                             (double)g.Cout * g.Cin * g.KH * g.KW * a.npairs);
+    ProfScope prof(MODE == MODE_FWD ? "conv_fwd" : "conv_dgrad", 2.0 * macs * a.npairs, io, st);
     if (Cd <= 16) {
         dim3 grid(cdiv(J, 256), cdiv(Cd, 16));
         conv_gather_gemm_kernel<16, 256, 16, 4, 4, MODE><<<grid, 256, 0, st>>>(a);
@@ -364,6 +368,9 @@ int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const floa
     a.npairs = npairs;
     for (int p = 0; p < npairs; ++p) { a.act[p] = act[p]; a.wt[p] = adj[p]; a.scale[p] = scale[p]; }
     a.out = wbar;
+    const double macs = (double)g.batch * g.OH * g.OW * g.Cout * g.Cin * g.KH * g.KW;
+    ProfScope prof("conv_wgrad", 2.0 * macs * npairs,
+                   4.0 * npairs * ((double)g.batch * g.Cin * g.H * g.W + (double)g.batch * g.Cout * g.OH * g.OW), st);
     const int Ncol = g.Cin * g.KH * g.KW;
     const long long J = (long long)g.batch * g.OH * g.OW;
     constexpr int BK = 32;
@@ -400,6 +407,7 @@ int launch_bias_grad(cudaStream_t st, const float* adj, int batch, int C, int HW
     const int cap = (4 * kNumSMs + C - 1) / C;
     if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;
+    ProfScope prof("bias_grad", (double)batch * C * HW, 4.0 * batch * C * HW, st);
     dim3 grid(C, splits);
     bias_grad_kernel<<<grid, 256, 0, st>>>(adj, batch, C, HW, sstride, bbar);
     B2S_LAUNCH_CHECK();

@@ -178,6 +178,7 @@ __global__ void sub_cast_kernel(const float* __restrict__ a, const float* __rest
 static inline long long per_sample(const View& v) { return (long long)v.C * v.H * v.W; }
 
 int launch_relu_fwd(cudaStream_t st, int order, const View& x0, const View& xk, const View& yk, int batch) {
+    ProfScope prof("relu_fwd", 0.0, 8.0 * batch * (double)yk.C * yk.H * yk.W, st);
     const long long per = per_sample(yk);
     relu_fwd_kernel<<<ew_grid(per, batch), 256, 0, st>>>(order, x0.p, x0.sstride, xk.p, xk.sstride, yk.p,
                                                           yk.sstride, per);
@@ -186,6 +187,7 @@ int launch_relu_fwd(cudaStream_t st, int order, const View& x0, const View& xk, 
 }
 int launch_relu_bwd(cudaStream_t st, const View& ref0, const View& adj_out, const View& adj_in, int batch,
                     int accumulate) {
+    ProfScope prof("relu_bwd", 0.0, 12.0 * batch * (double)adj_in.C * adj_in.H * adj_in.W, st);
     const long long per = per_sample(adj_in);
     relu_bwd_kernel<<<ew_grid(per, batch), 256, 0, st>>>(ref0.p, ref0.sstride, adj_out.p, adj_out.sstride,
                                                           adj_in.p, adj_in.sstride, per, accumulate);
@@ -193,6 +195,7 @@ int launch_relu_bwd(cudaStream_t st, const View& ref0, const View& adj_out, cons
     return 0;
 }
 int launch_mask_inplace(cudaStream_t st, const View& ref0, const View& adj, int batch) {
+    ProfScope prof("relu_mask", 0.0, 12.0 * batch * (double)adj.C * adj.H * adj.W, st);
     const long long per = per_sample(adj);
     mask_inplace_kernel<<<ew_grid(per, batch), 256, 0, st>>>(ref0.p, ref0.sstride, adj.p, adj.sstride, per);
     B2S_LAUNCH_CHECK();
@@ -200,6 +203,7 @@ int launch_mask_inplace(cudaStream_t st, const View& ref0, const View& adj, int 
 }
 int launch_maxpool_fwd(cudaStream_t st, int order, const View& xk, const View& yk, int32_t* argmax, int batch,
                        int kh, int kw, int sh, int sw, int ph, int pw) {
+    ProfScope prof("maxpool_fwd", 0.0, 4.0 * batch * ((double)xk.C * xk.H * xk.W + 2.0 * yk.C * yk.H * yk.W), st);
     const long long per = per_sample(yk);
     maxpool_fwd_kernel<<<ew_grid(per, batch, 256, 1), 256, 0, st>>>(order, xk.p, xk.sstride, yk.p, yk.sstride,
                                                                      argmax, xk.C, xk.H, xk.W, yk.H, yk.W, kh,
@@ -209,6 +213,7 @@ int launch_maxpool_fwd(cudaStream_t st, int order, const View& xk, const View& y
 }
 int launch_maxpool_bwd(cudaStream_t st, const View& adj_out, const View& adj_in, const int32_t* argmax,
                        int batch) {
+    ProfScope prof("maxpool_bwd", 0.0, 4.0 * batch * ((double)adj_in.C * adj_in.H * adj_in.W + 2.0 * adj_out.C * adj_out.H * adj_out.W), st);
     const long long per = per_sample(adj_out);
     maxpool_bwd_kernel<<<ew_grid(per, batch, 256, 1), 256, 0, st>>>(adj_out.p, adj_out.sstride, adj_in.p,
                                                                      adj_in.sstride, argmax, adj_in.C,
@@ -218,6 +223,7 @@ int launch_maxpool_bwd(cudaStream_t st, const View& adj_out, const View& adj_in,
     return 0;
 }
 int launch_avgpool_fwd(cudaStream_t st, const View& x, const View& y, int batch, int k) {
+    ProfScope prof("avgpool_fwd", 0.0, 4.0 * batch * ((double)x.C * x.H * x.W + (double)y.C * y.H * y.W), st);
     const long long per = per_sample(y);
     avgpool_fwd_kernel<<<ew_grid(per, batch, 256, 1), 256, 0, st>>>(x.p, x.sstride, y.p, y.sstride, x.C, x.H,
                                                                      x.W, y.H, y.W, k);
@@ -226,6 +232,7 @@ int launch_avgpool_fwd(cudaStream_t st, const View& x, const View& y, int batch,
 }
 int launch_avgpool_bwd(cudaStream_t st, const View& adj_out, const View& adj_in, int batch, int k,
                        int accumulate) {
+    ProfScope prof("avgpool_bwd", 0.0, 4.0 * batch * ((double)adj_in.C * adj_in.H * adj_in.W + (double)adj_out.C * adj_out.H * adj_out.W), st);
     const long long per = per_sample(adj_in);
     avgpool_bwd_kernel<<<ew_grid(per, batch), 256, 0, st>>>(adj_out.p, adj_out.sstride, adj_in.p,
                                                              adj_in.sstride, adj_in.C, adj_in.H, adj_in.W,
@@ -234,6 +241,7 @@ int launch_avgpool_bwd(cudaStream_t st, const View& adj_out, const View& adj_in,
     return 0;
 }
 int launch_copy_view(cudaStream_t st, const View& src, const View& dst, int batch, int accumulate) {
+    ProfScope prof("copy_view", 0.0, 8.0 * batch * (double)dst.C * dst.H * dst.W, st);
     const long long per = per_sample(dst);
     copy_view_kernel<<<ew_grid(per, batch), 256, 0, st>>>(src.p, src.sstride, dst.p, dst.sstride, per,
                                                            accumulate);
@@ -241,6 +249,7 @@ int launch_copy_view(cudaStream_t st, const View& src, const View& dst, int batc
     return 0;
 }
 int launch_zero_view(cudaStream_t st, const View& v, int batch) {
+    ProfScope prof("zero_view", 0.0, 4.0 * batch * (double)v.C * v.H * v.W, st);
     const long long per = per_sample(v);
     zero_view_kernel<<<ew_grid(per, batch), 256, 0, st>>>(v.p, v.sstride, per);
     B2S_LAUNCH_CHECK();

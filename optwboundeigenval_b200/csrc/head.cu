@@ -121,6 +121,7 @@ int launch_head(cudaStream_t st, int order, const HeadArgs& a) {
         set_error("loss head supports at most %d classes, got %d", kMaxClasses, a.C);
         return -4;
     }
+    ProfScope prof("loss_head", 0.0, 4.0 * a.batch * a.C * (order + 2), st);
     const int blocks = cdiv(a.batch, 128);
     if (order == 0) head_kernel<0><<<blocks, 128, 0, st>>>(a);
     else if (order == 1) head_kernel<1><<<blocks, 128, 0, st>>>(a);

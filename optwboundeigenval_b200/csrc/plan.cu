@@ -38,6 +38,29 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+struct ProfRec {
+    const char* name;
+    double flops, bytes;
+    cudaEvent_t e0, e1;
+};
+struct Profiler {
+    std::vector<ProfRec> recs;
+};
+static thread_local Profiler* g_prof = nullptr;
+
+ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t stream) : idx(-1), st(stream) {
+    if (!g_prof) return;
+    ProfRec r{name, flops, bytes, nullptr, nullptr};
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    g_prof->recs.push_back(r);
+    idx = (int)g_prof->recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0 && g_prof) cudaEventRecord(g_prof->recs[idx].e1, st);
+}
+
 void count_launch(int n) {
     g_capture_count += n;
     if (g_counting_paused) return;
@@ -142,8 +165,8 @@ static int alloc_order(b2s_plan* p, int k) {
     const size_t bytes = (size_t)p->arena_elems * sizeof(float);
     B2S_CUDA(cudaMalloc(&p->fw[k], bytes));
     B2S_CUDA(cudaMalloc(&p->bw[k], bytes));
-    B2S_CUDA(cudaMemset(p->fw[k], 0, bytes));
-    B2S_CUDA(cudaMemset(p->bw[k], 0, bytes));
+    B2S_CUDA(cudaMemsetAsync(p->fw[k], 0, bytes, p->stream));
+    B2S_CUDA(cudaMemsetAsync(p->bw[k], 0, bytes, p->stream));
     B2S_CUDA(cudaMalloc(&p->out32[k], (size_t)(p->P + 4) * sizeof(float)));
     p->workspace += 2 * (long long)bytes + (p->P + 4) * 4;
     if (p->bn_total > 0) {
@@ -640,7 +663,8 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
         set_error("b2s_plan_create: out of device memory: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(-2);
     }
-    cudaMemset(p->v32, 0, (size_t)(n_params + 4) * sizeof(float));
+    cudaMemsetAsync(p->v32, 0, (size_t)(n_params + 4) * sizeof(float), p->stream);
+    cudaMemsetAsync(p->params, 0, (size_t)(n_params + 4) * sizeof(float), p->stream);
     p->workspace += 2 * (n_params + 4) * 4 + (long long)lab * 8;
     for (int i = 0; i < n_ops; ++i) {
         if (ops[i].kind == B2S_OP_MAXPOOL) {
@@ -802,6 +826,52 @@ int b2s_debug_read(b2s_plan* p, int32_t adjoint, int32_t order, int32_t tensor, 
     B2S_CUDA(cudaMemcpy2D(h_out, n * sizeof(float), tptr(p, arena, order, tensor), (size_t)T.sample_stride * sizeof(float),
                           n * sizeof(float), (size_t)p->batch, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+int b2s_profile_pass(b2s_plan* p, int32_t order, int32_t reps, b2s_prof_entry* out, int32_t cap, int32_t* n_out) {
+    if (!p || !out || !n_out || order < 0 || order > 3 || reps <= 0) { set_error("b2s_profile_pass: invalid arguments"); return -1; }
+    if (p->batch <= 0) { set_error("b2s_profile_pass: call b2s_base_pass first"); return -1; }
+    if (order == 3 && !p->out_corr) { set_error("b2s_profile_pass: run b2s_vghv once before profiling the compatibility sweep"); return -1; }
+    B2S_TRY(enter(p));
+    if (order < 3) B2S_TRY(alloc_order(p, order));
+    Profiler prof;
+    int rc = 0;
+    rc = run_pass_eager(p, order);                   // warm-up, untimed
+    if (rc == 0) {
+        g_prof = &prof;
+        for (int r = 0; r < reps && rc == 0; ++r) rc = run_pass_eager(p, order);
+        g_prof = nullptr;
+    }
+    cudaStreamSynchronize(p->stream);
+    std::map<std::string, b2s_prof_entry> agg;
+    std::vector<std::string> order_seen;
+    for (auto& r : prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        auto it = agg.find(r.name);
+        if (it == agg.end()) {
+            b2s_prof_entry e{};
+            snprintf(e.name, sizeof(e.name), "%s", r.name);
+            it = agg.emplace(r.name, e).first;
+            order_seen.push_back(r.name);
+        }
+        it->second.launches += 1;
+        it->second.ms += ms;
+        it->second.flops += r.flops;
+        it->second.bytes += r.bytes;
+    }
+    int n = 0;
+    for (auto& name : order_seen) {
+        if (n >= cap) break;
+        b2s_prof_entry e = agg[name];
+        e.launches /= reps; e.ms /= reps; e.flops /= reps; e.bytes /= reps;
+        out[n++] = e;
+    }
+    *n_out = n;
+    if (rc != 0) return rc;
+    return leave(p);
 }
 
 const float* b2s_grad_f32(const b2s_plan* p) { return p ? p->out32[0] : nullptr; }

@@ -187,6 +187,21 @@ class SpectralPlan:
         out.trajectory = traj[:out.iters + 1] if traj is not None else None
         return out
 
+    def set_bn_third_order(self, exact: bool):
+        """False (default): reproduce nested torch.autograd's third-order BatchNorm result; True: exact."""
+        _lib.check(self.lib.b2s_plan_set_bn_third_order(self.handle, 1 if exact else 0))
+
+    def profile(self, order: int, reps: int = 3):
+        """Per kernel family: launches / ms / algorithmic FLOPs and bytes of one pass (CUDA events on the
+        launching stream around every kernel)."""
+        self._bind_stream()
+        cap = 64
+        arr = (_lib.ProfEntry * cap)()
+        n = ctypes.c_int32(0)
+        _lib.check(self.lib.b2s_profile_pass(self.handle, order, reps, arr, cap, ctypes.byref(n)), "b2s_profile_pass")
+        return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, flops=arr[i].flops,
+                     bytes=arr[i].bytes) for i in range(n.value)]
+
     # ---- data parallelism ---------------------------------------------------------------------
     def init_comm(self):
         """One NCCL communicator per plan, bootstrapped through torch.distributed (already initialised)."""
@@ -289,9 +304,9 @@ class B200HVPOperator(object):
         self.plan = plan_for(self.model, self.criterion, inputs, self.device)
         start = time.time()
         grad, loss = self.plan.base_pass(flat_parameters(self.model), inputs, target)
-        for m in self.plan.tape.bn_modules:          # train-mode forward side effect
-            if m.num_batches_tracked is not None:
-                m.num_batches_tracked += 1
+        nbt = [m.num_batches_tracked for m in self.plan.tape.bn_modules if m.num_batches_tracked is not None]
+        if nbt:                                       # train-mode forward side effect
+            torch._foreach_add_(nbt, 1)
         self.aTime0 += time.time() - start
         self.loss_value = loss
         return grad

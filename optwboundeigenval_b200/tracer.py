@@ -630,6 +630,16 @@ def _finish(b: _Builder, result: int, head: int, input_shape) -> Tape:
     # every op output adjoint must have been written by someone (its consumers) before the op runs backward:
     # guaranteed by topological order as long as each tensor has at least one consumer.
 
+    # tensors that no longer exist (fused ReLU outputs, unused nodes) alias their replacement so the
+    # table stays valid
+    for t, vt in enumerate(vts):
+        if vt.buf < 0:
+            r = resolve(t)
+            if r != t and vts[r].buf >= 0:
+                vt.buf, vt.offset = vts[r].buf, vts[r].offset
+            else:
+                vt.buf, vt.offset, vt.shape = 0, 0, (1, 1, 1)
+
     conv_layers, seen = [], set()
     for i, op in enumerate(ops):
         if op.kind == OP_CONV and id(op.module) not in seen:

