@@ -220,12 +220,8 @@ def test_vector_kernels_against_the_reference_loop():
         dg, qg = d.cuda(), q.cuda()
         v32 = lib.b2s_pi_v32(st)
         for _ in range(25):
-            buf = (ctypes.c_float * n).from_address(v32)
-            v = torch.empty(n, dtype=torch.float32, device="cuda")
             torch.cuda.synchronize()
-            # read the library's fp32 vector through a tensor view of its device pointer
-            import torch.utils.dlpack  # noqa: F401
-            vv = _as_tensor(v32, n)
+            vv = _as_tensor(v32, n)      # the library's fp32 vector, viewed in place
             hv = (dg * vv.double() + 0.5 * qg * torch.dot(qg, vv.double())).float().contiguous()
             torch.cuda.synchronize()
             _lib.check(lib.b2s_pi_step(st, ctypes.c_void_p(hv.data_ptr()), None))
