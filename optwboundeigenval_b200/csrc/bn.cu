@@ -66,7 +66,7 @@ __device__ __forceinline__ Jet<K, float> load_jet(const float* const* p, long lo
 
 static inline dim3 bn_grid(const BnArgs& a) {
     const long long total = (long long)a.batch * a.HW;
-    long long splits = (total + 256 * 8 - 1) / (256 * 8);
+    long long splits = (total + 256 * 2 - 1) / (256 * 2);
     long long cap = (8LL * kNumSMs + a.C - 1) / a.C;
     if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;

@@ -177,6 +177,221 @@ conv_gather_gemm_kernel(const ConvKArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad for FEW destination channels (DenseNet growth convs: 48->12 3x3, Cin->48 1x1 and
+// their transposes).  One thread per destination pixel keeps MT destination channels in registers;
+// warps of a CTA split the destination channels (groups) and the source channels (K slices), the
+// slices are summed through shared memory.  Weights of one (activation, weight) pair are staged in
+// shared memory as [k][m] so that a thread reads its MT weights with 128-bit broadcast loads.
+// Replaces the tile kernel where its grid collapses (8..128 CTAs for the 8x8 / 16x16 maps).
+// ---------------------------------------------------------------------------------------------
+template <int MT, int KHW_T, int MODE>
+__global__ void __launch_bounds__(512)
+conv_px_kernel(const ConvKArgs a, const int groups, const int slices, const int pw_count) {
+    extern __shared__ __align__(16) float px_smem[];
+    const ConvGeom& g = a.g;
+    const int Cd = MODE == MODE_FWD ? g.Cout : g.Cin;
+    const int Hd = MODE == MODE_FWD ? g.OH : g.H;
+    const int Wd = MODE == MODE_FWD ? g.OW : g.W;
+    const long long d_ss = MODE == MODE_FWD ? g.out_sstride : g.in_sstride;
+    const int Cs = MODE == MODE_FWD ? g.Cin : g.Cout;
+    const int Hs = MODE == MODE_FWD ? g.H : g.OH;
+    const int Ws = MODE == MODE_FWD ? g.W : g.OW;
+    const long long s_ss = MODE == MODE_FWD ? g.in_sstride : g.out_sstride;
+    const int KHW = KHW_T > 0 ? KHW_T : g.KH * g.KW;
+    const int Ktot = Cs * KHW;
+    const int HWd = Hd * Wd, HWs = Hs * Ws;
+    const long long J = (long long)g.batch * HWd;
+    const int Mpad = groups * MT;
+    float* Wsm = px_smem;                       // [Ktot][Mpad]
+    float* red = px_smem + (size_t)Ktot * Mpad; // [pw_count][Mpad][32]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pw = warp % pw_count;
+    const int gi = (warp / pw_count) % groups;
+    const int sl = warp / (pw_count * groups);
+    const long long j = ((long long)blockIdx.x * pw_count + pw) * 32 + lane;
+    const bool ok = j < J;
+    int n = 0, y = 0, x = 0, pix = 0;
+    if (ok) {
+        n = (int)(j / HWd);
+        pix = (int)(j - (long long)n * HWd);
+        y = pix / Wd;
+        x = pix - y * Wd;
+    }
+    // per-thread tap table (offset inside a source channel plane, -1 when the tap falls outside)
+    int toff[KHW_T > 0 ? KHW_T : 1];
+    if (KHW_T > 0) {
+#pragma unroll
+        for (int t = 0; t < (KHW_T > 0 ? KHW_T : 1); ++t) {
+            const int ky = t / g.KW, kx = t - ky * g.KW;
+            int sy, sx;
+            bool v;
+            if (MODE == MODE_FWD) {
+                sy = y * g.sh + ky - g.ph; sx = x * g.sw + kx - g.pw;
+                v = sy >= 0 && sy < Hs && sx >= 0 && sx < Ws;
+            } else {
+                const int ty_ = y + g.ph - ky, tx_ = x + g.pw - kx;
+                sy = ty_ / g.sh; sx = tx_ / g.sw;
+                v = ty_ >= 0 && tx_ >= 0 && sy * g.sh == ty_ && sx * g.sw == tx_ && sy < Hs && sx < Ws;
+            }
+            toff[t] = (ok && v) ? sy * Ws + sx : -1;
+        }
+    }
+
+    float acc[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+
+    for (int p = 0; p < a.npairs; ++p) {
+        __syncthreads();
+        const float* __restrict__ wt = a.wt[p];
+        const float sc = a.scale[p];
+        for (int idx = tid; idx < Ktot * Mpad; idx += blockDim.x) {
+            const int k = idx / Mpad, m = idx - k * Mpad;
+            float v = 0.f;
+            if (m < Cd) {
+                if (MODE == MODE_FWD) v = wt[(long long)m * Ktot + k];
+                else { const int c = k / KHW, t = k - c * KHW; v = wt[((long long)c * g.Cin + m) * KHW + t]; }
+            }
+            Wsm[idx] = v * sc;
+        }
+        __syncthreads();
+        const float* __restrict__ src = a.act[p] + (long long)n * s_ss;
+        for (int c = sl; c < Cs; c += slices) {
+            const float* __restrict__ sc_ = src + (long long)c * HWs;
+            const float* wbase = Wsm + (size_t)c * KHW * Mpad + gi * MT;
+            if (KHW_T > 0) {
+                float xv[KHW_T > 0 ? KHW_T : 1];
+#pragma unroll
+                for (int t = 0; t < (KHW_T > 0 ? KHW_T : 1); ++t) xv[t] = toff[t] >= 0 ? sc_[toff[t]] : 0.f;
+#pragma unroll
+                for (int t = 0; t < (KHW_T > 0 ? KHW_T : 1); ++t) {
+                    const float4* w4 = reinterpret_cast<const float4*>(wbase + t * Mpad);
+#pragma unroll
+                    for (int q = 0; q < MT / 4; ++q) {
+                        const float4 w = w4[q];
+                        acc[4 * q + 0] = fmaf(w.x, xv[t], acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(w.y, xv[t], acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(w.z, xv[t], acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(w.w, xv[t], acc[4 * q + 3]);
+                    }
+                }
+            } else {
+                for (int ky = 0; ky < g.KH; ++ky)
+                    for (int kx = 0; kx < g.KW; ++kx) {
+                        int sy, sx;
+                        bool v;
+                        if (MODE == MODE_FWD) {
+                            sy = y * g.sh + ky - g.ph; sx = x * g.sw + kx - g.pw;
+                            v = sy >= 0 && sy < Hs && sx >= 0 && sx < Ws;
+                        } else {
+                            const int ty_ = y + g.ph - ky, tx_ = x + g.pw - kx;
+                            sy = ty_ / g.sh; sx = tx_ / g.sw;
+                            v = ty_ >= 0 && tx_ >= 0 && sy * g.sh == ty_ && sx * g.sw == tx_ && sy < Hs && sx < Ws;
+                        }
+                        const float xv = (ok && v) ? sc_[sy * Ws + sx] : 0.f;
+                        const float4* w4 = reinterpret_cast<const float4*>(wbase + (ky * g.KW + kx) * Mpad);
+#pragma unroll
+                        for (int q = 0; q < MT / 4; ++q) {
+                            const float4 w = w4[q];
+                            acc[4 * q + 0] = fmaf(w.x, xv, acc[4 * q + 0]);
+                            acc[4 * q + 1] = fmaf(w.y, xv, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(w.z, xv, acc[4 * q + 2]);
+                            acc[4 * q + 3] = fmaf(w.w, xv, acc[4 * q + 3]);
+                        }
+                    }
+            }
+        }
+    }
+    // ---- sum the K slices (fixed order: deterministic) -------------------------------------------
+    float* myred = red + ((size_t)pw * Mpad + gi * MT) * 32 + lane;
+    for (int r = 0; r < slices; ++r) {
+        if (sl == r) {
+            if (r == 0) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) myred[m * 32] = acc[m];
+            } else {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) myred[m * 32] += acc[m];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: slice `sl` of each (pixel warp, group) writes channels mm = sl, sl+slices, ...
+    if (!ok) return;
+    const long long base = (long long)n * d_ss + pix;
+    for (int mm = sl; mm < MT; mm += slices) {
+        const int m = gi * MT + mm;
+        if (m >= Cd) break;
+        const long long o = base + (long long)m * HWd;
+        float v = myred[mm * 32];
+        if (a.bias) v += a.bias[m];
+        if (a.accumulate) v += a.out[o];
+        if (a.relu_mode == 1) v = v > 0.f ? v : 0.f;
+        else if (a.relu_mode == 2) v = a.relu_ref[o] > 0.f ? v : 0.f;
+        a.out[o] = v;
+    }
+}
+
+template <int MT, int MODE>
+static int launch_px_t(cudaStream_t st, const ConvKArgs& a, int groups, int slices, int pw, int khw, size_t smem,
+                       int blocks) {
+    const int threads = 32 * pw * groups * slices;
+#define B2S_PX_LAUNCH(KT)                                                                                  \
+    do {                                                                                                   \
+        if (smem > 48 * 1024)                                                                              \
+            cudaFuncSetAttribute(conv_px_kernel<MT, KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                              \
+        conv_px_kernel<MT, KT, MODE><<<blocks, threads, smem, st>>>(a, groups, slices, pw);                \
+    } while (0)
+    if (khw == 1) B2S_PX_LAUNCH(1);
+    else if (khw == 9) B2S_PX_LAUNCH(9);
+    else B2S_PX_LAUNCH(0);
+#undef B2S_PX_LAUNCH
+    return 0;
+}
+
+// returns true when the pixel-thread kernel was used
+template <int MODE>
+static bool try_launch_px(cudaStream_t st, const ConvKArgs& a) {
+    const ConvGeom& g = a.g;
+    const int Cd = MODE == MODE_FWD ? g.Cout : g.Cin;
+    const int Cs = MODE == MODE_FWD ? g.Cin : g.Cout;
+    const int khw = g.KH * g.KW;
+    const long long J = (long long)g.batch * (MODE == MODE_FWD ? g.OH * g.OW : g.H * g.W);
+    if (Cd > 160) return false;
+    // register block: least padding, then the widest
+    const int cand[5] = {32, 24, 16, 12, 8};
+    int MT = 8, best_pad = 1 << 30;
+    for (int c : cand) {
+        const int pad = (Cd + c - 1) / c * c;
+        if (pad < best_pad) { best_pad = pad; MT = c; }
+    }
+    const int groups = best_pad / MT;
+    if (groups > 16) return false;
+    const size_t wbytes = (size_t)Cs * khw * best_pad * sizeof(float);
+    if (wbytes > 160 * 1024) return false;
+    int pw = 4;
+    while (pw > 1 && (pw * groups > 16 || J / (32 * pw) < 2 * kNumSMs)) pw >>= 1;
+    if (pw * groups > 16) return false;
+    int slices = 16 / (pw * groups);
+    if (slices > Cs) slices = Cs;
+    if (slices < 1) slices = 1;
+    const size_t smem = wbytes + (size_t)pw * best_pad * 32 * sizeof(float);
+    if (smem > 200 * 1024) return false;
+    const int blocks = (int)((J + 32 * pw - 1) / (32 * pw));
+    switch (MT) {
+    case 32: launch_px_t<32, MODE>(st, a, groups, slices, pw, khw, smem, blocks); break;
+    case 24: launch_px_t<24, MODE>(st, a, groups, slices, pw, khw, smem, blocks); break;
+    case 16: launch_px_t<16, MODE>(st, a, groups, slices, pw, khw, smem, blocks); break;
+    case 12: launch_px_t<12, MODE>(st, a, groups, slices, pw, khw, smem, blocks); break;
+    default: launch_px_t<8, MODE>(st, a, groups, slices, pw, khw, smem, blocks); break;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // wgrad: Wbar[m, (c,ky,kx)] += sum_j adj[n, m, oy, ox] * act[n, c, oy*sh+ky-ph, ox*sw+kx-pw]
 // ---------------------------------------------------------------------------------------------
@@ -326,6 +541,10 @@ static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
     const double io = 4.0 * ((double)g.batch * g.Cin * g.H * g.W * a.npairs + (double)g.batch * g.Cout * g.OH * g.OW +
                              (double)g.Cout * g.Cin * g.KH * g.KW * a.npairs);
     ProfScope prof(MODE == MODE_FWD ? "conv_fwd" : "conv_dgrad", 2.0 * macs * a.npairs, io, st);
+    if (try_launch_px<MODE>(st, a)) {
+        B2S_LAUNCH_CHECK();
+        return 0;
+    }
     if (Cd <= 16) {
         dim3 grid(cdiv(J, 256), cdiv(Cd, 16));
         conv_gather_gemm_kernel<16, 256, 16, 4, 4, MODE><<<grid, 256, 0, st>>>(a);

@@ -1,0 +1,86 @@
+"""Run a reference parameter file through the B200 path:  the equivalent of ``python main.py <pfile>``
+(reference main.py:16-19) with the drop-in installed.
+
+    python -m optwboundeigenval_b200.main <pfile> --reference /path/to/optWBoundEigenval \
+        [--offline] [--set key=value ...] [--workdir DIR] [--no-install]
+
+``--offline`` substitutes seeded synthetic data for the data modules (no network / private paths) and
+builds torchvision backbones without downloading weights.  ``--set`` overrides entries of the
+options dict (e.g. ``--set train=True max_iter=1 test=False``) -- several parameter files ship with
+``train=False`` and only run analysis code.  ``--no-install`` runs the unmodified
+reference (CPU autograd) through the same harness, for side-by-side comparison.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import os
+import sys
+import tempfile
+
+
+def run(pfile, reference, offline=False, overrides=None, workdir=None, install=True):
+    from . import dropin
+    reference = os.path.abspath(reference)
+    if not os.path.exists(os.path.join(reference, "opt.py")):
+        raise FileNotFoundError("no opt.py under %s" % reference)
+    dropin.stub_plotting_modules()
+    if reference not in sys.path:
+        sys.path.insert(0, reference)
+    import opt  # noqa: E402  (the reference module)
+    if offline:
+        dropin.offline_shims(reference)
+    if install:
+        dropin.install(opt)
+    workdir = workdir or tempfile.mkdtemp(prefix="b200_run_")
+    os.makedirs(workdir, exist_ok=True)
+    link = os.path.join(workdir, "params")
+    if not os.path.exists(link):
+        os.symlink(os.path.join(reference, "params"), link)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        sys.path.insert(0, "./params")
+        params = __import__(pfile)
+        if overrides:
+            orig = params.options
+
+            def options():
+                d = orig()
+                d.update(overrides)
+                return d
+            params.options = options
+        opt.main(pfile)
+    finally:
+        os.chdir(cwd)
+        if install:
+            dropin.uninstall(opt)
+    return workdir
+
+
+def _parse_overrides(items):
+    out = {}
+    for it in items or []:
+        k, v = it.split("=", 1)
+        try:
+            out[k] = ast.literal_eval(v)
+        except (ValueError, SyntaxError):
+            out[k] = v
+    return out
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument("pfile")
+    ap.add_argument("--reference", default=os.environ.get("OPTW_REFERENCE", "."))
+    ap.add_argument("--offline", action="store_true")
+    ap.add_argument("--set", nargs="*", default=[])
+    ap.add_argument("--workdir", default=None)
+    ap.add_argument("--no-install", action="store_true")
+    a = ap.parse_args(argv)
+    wd = run(a.pfile, a.reference, a.offline, _parse_overrides(a.set), a.workdir, not a.no_install)
+    print("logs and models under", wd)
+
+
+if __name__ == "__main__":
+    main()

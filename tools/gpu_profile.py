@@ -34,9 +34,9 @@ def main():
         tot = sum(r["ms"] for r in rows)
         print("--- pass %s: %.3f ms in kernels, %d launches" % (label, tot, sum(r["launches"] for r in rows)))
         for r in sorted(rows, key=lambda r: -r["ms"]):
-            gf = r["flops"] / r["ms"] / 1e9 if r["ms"] > 0 else 0
+            gf = r["flops"] / r["ms"] / 1e9 if r["ms"] > 0 else 0   # TFLOP/s
             gb = r["bytes"] / r["ms"] / 1e6 if r["ms"] > 0 else 0
-            print("   %-16s launches %4d  %8.3f ms (%5.1f%%)  %9.1f GFLOP/s  %8.1f GB/s" % (
+            print("   %-16s launches %4d  %8.3f ms (%5.1f%%)  %9.2f TFLOP/s  %8.1f GB/s" % (
                 r["name"], r["launches"], r["ms"], 100 * r["ms"] / tot, gf, gb))
     # wall clock of the graph-replayed HVP
     for _ in range(3):
