@@ -199,6 +199,22 @@ int b2s_pi_done(b2s_pistate* s, void* stream);
 int b2s_pi_result(b2s_pistate* s, b2s_power_result* h_result, double* h_traj, double* d_v_out,
                   void* stream);
 
+/* ---- K-FAC preconditioner of the `lobpcg=True` variant (opt.py:362-416) ---------------------
+ * Layers are named by the index of their Conv/Linear op in the tape.  b2s_kfac_build forms, from the
+ * cached base pass of the current batch, A = 0.95 I + 0.05 E[a a^T] of op_a's input patches (bias
+ * column of ones; kfac.py:292-311,52-58) and G = 0.95 I + 0.05 B*S*sum(g g^T) of op_g's output
+ * adjoint (kfac.py:337-367,60-65) into caller-provided device buffers [da,da] / [dg,dg] (op_a / op_g
+ * differ only for a module applied twice: last forward use for A, first for G, as the reference's
+ * hooks leave them).  The host runs eigh on them (kfac.py:87-93) and installs the two inverses
+ * Q diag(1/d) Q^T (borrowed device pointers, row-major fp32) with b2s_kfac_set.  b2s_kfac_apply maps
+ * r -> T r = G^-1 R A^-1 per layer, identity elsewhere (opt.py:384-416, kfac.py:118-120);
+ * b2s_power_iterate with cfg.precond = 1 uses it for v <- normalise(v + alpha T r) (opt.py:491-498). */
+int b2s_kfac_dims(const b2s_plan* p, int32_t op_index, int32_t* dim_a, int32_t* dim_g);
+int b2s_kfac_build(b2s_plan* p, int32_t op_a, int32_t op_g, float* d_A, float* d_G);
+int b2s_kfac_clear(b2s_plan* p);
+int b2s_kfac_set(b2s_plan* p, int32_t op_index, const float* d_Ainv, const float* d_Ginv);
+int b2s_kfac_apply(b2s_plan* p, const double* d_r, double* d_out);
+
 /* ---- data parallelism (one process per GPU) ------------------------------------------- */
 int b2s_comm_unique_id(void* h_id128);                       /* 128 bytes, rank 0 */
 int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world);

@@ -61,6 +61,11 @@ SIGNATURES = {
     "b2s_pi_precond_update": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_pi_done": (c_int32, [c_void_p, c_void_p]),
     "b2s_pi_result": (c_int32, [c_void_p, POINTER(PowerResult), c_void_p, c_void_p, c_void_p]),
+    "b2s_kfac_dims": (c_int32, [c_void_p, c_int32, POINTER(c_int32), POINTER(c_int32)]),
+    "b2s_kfac_build": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2s_kfac_clear": (c_int32, [c_void_p]),
+    "b2s_kfac_set": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "b2s_kfac_apply": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_comm_unique_id": (c_int32, [c_void_p]),
     "b2s_comm_init": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
     "b2s_comm_destroy": (c_int32, [c_void_p]),

@@ -104,4 +104,13 @@ struct HeadArgs {
 };
 int launch_head(cudaStream_t st, int order, const HeadArgs& a);
 
+// ---- K-FAC preconditioner (kfac.cu) ------------------------------------------------------------
+int launch_gram(cudaStream_t st, const float* src, long long sstride, int batch, int C, int H, int W, int OH, int OW,
+                int KH, int KW, int sh, int sw, int ph, int pw, int has_ones, float elem_scale, float ones_value,
+                float scale, float diag_add, float* out);
+int launch_sgemm_small(cudaStream_t st, int M, int N, int K, const float* A, int a_rs, int a_cs, const float* B,
+                       int b_rs, int b_cs, float* C, int ldc);
+int launch_kfac_gather(cudaStream_t st, const double* r, long long w_off, long long b_off, int dg, int dw, float* M);
+int launch_kfac_scatter(cudaStream_t st, const float* M, long long w_off, long long b_off, int dg, int dw, double* out);
+
 }  // namespace b2s

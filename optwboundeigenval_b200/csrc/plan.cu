@@ -10,6 +10,7 @@
 //     order 2 -> grad_w (v^T H v)          (second half of vGHv, opt.py:110-152)
 // Each pass is a fixed kernel sequence, captured once per batch size into a CUDA graph and
 // replayed (one graph launch per HVP instead of the reference's per-op autograd dispatch).
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <map>
@@ -140,6 +141,17 @@ struct b2s_plan {
 
     std::map<long long, GraphEntry> graphs;   // key = order * 2^32 + batch
     bool v_is_current = false;        // order-1 caches correspond to the contents of v32
+
+    struct KfacLayer {
+        int op = -1;                  // op whose parameter slots / geometry the layer uses
+        int dg = 0, da = 0, dw = 0;
+        const float* Ainv = nullptr;  // [da,da] borrowed from the caller
+        const float* Ginv = nullptr;  // [dg,dg]
+    };
+    std::vector<KfacLayer> kfac;
+    float* kfac_m = nullptr;          // scratch [dg,da] x2
+    long long kfac_m_elems = 0;
+    double* kfac_tr = nullptr;        // T r
 
     b2s_pistate* pi = nullptr;
     Comm* comm = nullptr;
@@ -298,6 +310,7 @@ static int forward(b2s_plan* p, int K) {
     h.loss = K == 0 ? p->loss : nullptr;
     if (K == 0) B2S_CUDA(cudaMemsetAsync(p->loss, 0, sizeof(double), st));
     B2S_TRY(launch_head(st, K, h));
+    if (K == 0 && p->comm) B2S_TRY(comm_allreduce_f64(p->comm, p->loss, 1, st));
     return 0;
 }
 
@@ -693,6 +706,7 @@ int b2s_plan_destroy(b2s_plan* p) {
     }
     for (auto a : p->argmax) cudaFree(a);
     cudaFree(p->csum); cudaFree(p->out_corr);
+    cudaFree(p->kfac_m); cudaFree(p->kfac_tr);
     cudaFree(p->params); cudaFree(p->v32); cudaFree(p->loss);
     cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
     if (p->pi) b2s_pi_destroy(p->pi);
@@ -966,16 +980,18 @@ int b2s_pi_result(b2s_pistate* s, b2s_power_result* r, double* h_traj, double* d
     return pi_result_impl(s, r, h_traj, d_v_out, (cudaStream_t)stream);
 }
 
+static int kfac_apply_impl(b2s_plan* p, const double* d_r, double* d_out);
+
 int b2s_power_iterate(b2s_plan* p, double* d_v, const b2s_power_cfg* cfg, b2s_power_result* h_result,
                       double* h_traj) {
     if (!p || !d_v || !cfg) { set_error("b2s_power_iterate: null argument"); return -1; }
     if (p->batch <= 0) { set_error("b2s_power_iterate: call b2s_base_pass first"); return -1; }
-    if (cfg->precond) {
-        set_error("b2s_power_iterate: the preconditioned variant is driven through b2s_pi_step / "
-                  "b2s_pi_precond_update");
+    if (cfg->precond && p->kfac.empty()) {
+        set_error("b2s_power_iterate: precond = 1 but no K-FAC factors are installed (b2s_kfac_set)");
         return -1;
     }
     B2S_TRY(enter(p));
+    if (cfg->precond && !p->kfac_tr) B2S_CUDA(cudaMalloc(&p->kfac_tr, (size_t)(p->P + 4) * sizeof(double)));
     if (!p->pi || p->pi->cap < cfg->max_iter) {
         if (p->pi) { b2s_pi_destroy(p->pi); p->pi = nullptr; }
         const int cap = cfg->max_iter > 1024 ? cfg->max_iter : 1024;
@@ -991,10 +1007,113 @@ int b2s_power_iterate(b2s_plan* p, double* d_v, const b2s_power_cfg* cfg, b2s_po
         B2S_TRY(launch_pi_step(st, s->d, s->n, p->out32[1]));
         B2S_CUDA(cudaMemcpyAsync(&done, &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, st));
         B2S_CUDA(cudaStreamSynchronize(st));
+        if (cfg->precond && !done) {                          // v <- normalise(v + alpha T r)   opt.py:491-498
+            PiDev h;
+            B2S_CUDA(cudaMemcpyAsync(&h, s->d, sizeof(PiDev), cudaMemcpyDeviceToHost, st));
+            B2S_CUDA(cudaStreamSynchronize(st));
+            B2S_TRY(kfac_apply_impl(p, s->rbuf[h.r_last], p->kfac_tr));
+            B2S_TRY(launch_pi_precond_update(st, s->d, s->n, p->kfac_tr));
+            B2S_CUDA(cudaMemcpyAsync(&done, &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            B2S_CUDA(cudaStreamSynchronize(st));
+        }
     }
     p->v_is_current = false;
     B2S_TRY(pi_result_impl(s, h_result, h_traj, d_v, st));
     B2S_CUDA(cudaStreamSynchronize(st));
+    return leave(p);
+}
+
+// ---- K-FAC preconditioner ---------------------------------------------------------------------------
+static int kfac_dims(const b2s_plan* p, int op_index, int* da, int* dg, int* dw) {
+    if (!p || op_index < 0 || op_index >= (int)p->ops.size() || p->ops[op_index].kind != B2S_OP_CONV) {
+        set_error("b2s_kfac: op %d is not a Conv2d/Linear op", op_index);
+        return -1;
+    }
+    const b2s_op& op = p->ops[op_index];
+    const int w = p->tensors[op.in].C * op.kh * op.kw;
+    if (dw) *dw = w;
+    if (da) *da = w + (op.b_off >= 0 ? 1 : 0);
+    if (dg) *dg = p->tensors[op.out].C;
+    return 0;
+}
+
+int b2s_kfac_dims(const b2s_plan* p, int32_t op_index, int32_t* dim_a, int32_t* dim_g) {
+    return kfac_dims(p, op_index, dim_a, dim_g, nullptr);
+}
+
+int b2s_kfac_build(b2s_plan* p, int32_t op_a, int32_t op_g, float* d_A, float* d_G) {
+    int da = 0, dg = 0;
+    B2S_TRY(kfac_dims(p, op_a, &da, nullptr, nullptr));
+    B2S_TRY(kfac_dims(p, op_g, nullptr, &dg, nullptr));
+    if (!d_A || !d_G) { set_error("b2s_kfac_build: null output"); return -1; }
+    if (p->batch <= 0) { set_error("b2s_kfac_build: call b2s_base_pass first"); return -1; }
+    if (p->world > 1) { set_error("b2s_kfac_build: the preconditioned variant runs on one GPU"); return -1; }
+    B2S_TRY(enter(p));
+    cudaStream_t st = p->stream;
+    {   // A = 0.95 I + 0.05 a^T a / B, a = patches / spatial with a ones column (kfac.py:292-311, 52-58)
+        const b2s_op& op = p->ops[op_a];
+        const b2s_tensor& I = p->tensors[op.in];
+        const b2s_tensor& O = p->tensors[op.out];
+        const float S = (float)(O.H * O.W);
+        B2S_TRY(launch_gram(st, tptr(p, p->fw, 0, op.in), I.sample_stride, p->batch, I.C, I.H, I.W, O.H, O.W, op.kh, op.kw,
+                            op.sh, op.sw, op.ph, op.pw, op.b_off >= 0 ? 1 : 0, 1.f / S, 1.f / S,
+                            0.05f / (float)p->batch, 0.95f, d_A));
+    }
+    {   // G = 0.95 I + 0.05 * B*S * g^T g  (kfac.py:337-367 with batch_averaged=True, 60-65)
+        const b2s_op& op = p->ops[op_g];
+        const b2s_tensor& O = p->tensors[op.out];
+        const float S = (float)(O.H * O.W);
+        B2S_TRY(launch_gram(st, tptr(p, p->bw, 0, op.out), O.sample_stride, p->batch, O.C, O.H, O.W, O.H, O.W, 1, 1, 1, 1,
+                            0, 0, 0, 1.f, 0.f, 0.05f * (float)p->batch * S, 0.95f, d_G));
+    }
+    return leave(p);
+}
+
+int b2s_kfac_clear(b2s_plan* p) {
+    if (!p) return -1;
+    p->kfac.clear();
+    return 0;
+}
+
+int b2s_kfac_set(b2s_plan* p, int32_t op_index, const float* d_Ainv, const float* d_Ginv) {
+    b2s_plan::KfacLayer L;
+    B2S_TRY(kfac_dims(p, op_index, &L.da, &L.dg, &L.dw));
+    if (!d_Ainv || !d_Ginv) { set_error("b2s_kfac_set: null matrix"); return -1; }
+    L.op = op_index; L.Ainv = d_Ainv; L.Ginv = d_Ginv;
+    for (auto& e : p->kfac)
+        if (p->ops[e.op].w_off == p->ops[op_index].w_off) { e = L; return 0; }
+    p->kfac.push_back(L);
+    return 0;
+}
+
+static int kfac_apply_impl(b2s_plan* p, const double* d_r, double* d_out) {
+    cudaStream_t st = p->stream;
+    long long need = 0;
+    for (auto& L : p->kfac) need = std::max(need, (long long)L.dg * L.da);
+    if (need > p->kfac_m_elems) {
+        B2S_CUDA(cudaStreamSynchronize(st));
+        cudaFree(p->kfac_m);
+        B2S_CUDA(cudaMalloc(&p->kfac_m, (size_t)need * 2 * sizeof(float)));
+        p->kfac_m_elems = need;
+    }
+    if (d_out != d_r)
+        B2S_CUDA(cudaMemcpyAsync(d_out, d_r, (size_t)p->P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (auto& L : p->kfac) {
+        const b2s_op& op = p->ops[L.op];
+        float* M = p->kfac_m;
+        float* T = p->kfac_m + p->kfac_m_elems;
+        B2S_TRY(launch_kfac_gather(st, d_r, op.w_off, op.b_off, L.dg, L.dw, M));                 // opt.py:400-407
+        B2S_TRY(launch_sgemm_small(st, L.dg, L.da, L.dg, L.Ginv, L.dg, 1, M, L.da, 1, T, L.da));  // G^-1 R
+        B2S_TRY(launch_sgemm_small(st, L.dg, L.da, L.da, T, L.da, 1, L.Ainv, L.da, 1, M, L.da));  // (.) A^-1
+        B2S_TRY(launch_kfac_scatter(st, M, op.w_off, op.b_off, L.dg, L.dw, d_out));               // opt.py:409-411
+    }
+    return 0;
+}
+
+int b2s_kfac_apply(b2s_plan* p, const double* d_r, double* d_out) {
+    if (!p || !d_r || !d_out) { set_error("b2s_kfac_apply: null argument"); return -1; }
+    B2S_TRY(enter(p));
+    B2S_TRY(kfac_apply_impl(p, d_r, d_out));
     return leave(p);
 }
 

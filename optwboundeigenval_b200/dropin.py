@@ -37,8 +37,12 @@ def install(opt_module, fused_loop: bool = True, force_gpu: bool = True):
              "__init__": cls.__init__}
     opt_module.HVPOperator = B200HVPOperator
     if fused_loop:
+        from . import kfac as _kfac
+        saved.update({"kfac": cls.kfac, "init_kfac": cls.init_kfac})
         cls.comp_rho = spectral.comp_rho
         cls.comp_gradrho = spectral.comp_gradrho
+        cls.kfac = _kfac.kfac
+        cls.init_kfac = _kfac.init_kfac
     if force_gpu:
         orig_init = cls.__init__
 
@@ -69,6 +73,8 @@ def uninstall(opt_module):
     cls = opt_module.OptWBoundEignVal
     opt_module.HVPOperator = saved["HVPOperator"]
     cls.comp_rho, cls.comp_gradrho, cls.__init__ = saved["comp_rho"], saved["comp_gradrho"], saved["__init__"]
+    if "kfac" in saved:
+        cls.kfac, cls.init_kfac = saved["kfac"], saved["init_kfac"]
     del opt_module._b200_saved
 
 

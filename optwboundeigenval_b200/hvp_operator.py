@@ -163,13 +163,14 @@ class SpectralPlan:
         _lib.check(self.lib.b2s_vghv(self.handle, _ptr(v), _ptr(out)), "b2s_vghv")
         return out
 
-    def power_iterate(self, v0: torch.Tensor, eps: float, max_iter: int, alphas=None, want_trajectory=False):
+    def power_iterate(self, v0: torch.Tensor, eps: float, max_iter: int, alphas=None, want_trajectory=False,
+                      precond=False):
         self._bind_stream()
         v = v0.to(self.device, torch.float64).contiguous().clone()
         cfg = _lib.PowerCfg()
         cfg.max_iter = int(max_iter)
         cfg.eps = float(eps)
-        cfg.precond = 0
+        cfg.precond = 1 if precond else 0
         keep = None
         if alphas is not None:
             keep = (ctypes.c_double * int(max_iter))(*[float(a) for a in alphas])

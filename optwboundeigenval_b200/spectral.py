@@ -145,6 +145,14 @@ class SpectralState(object):
     comp_gradrho = comp_gradrho
     comp_g = comp_g
 
+    def kfac(self, r):            # opt.py:384-416
+        from .kfac import kfac as _kfac
+        return _kfac(self, r)
+
+    def init_kfac(self, data):    # opt.py:362-382
+        from .kfac import init_kfac as _init
+        return _init(self, data)
+
     def step_direction(self, data):
         """The assembly of iter() (opt.py:616-639): grad f + mu * sign * grad rho."""
         self.comp_g(data)

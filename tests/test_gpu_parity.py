@@ -288,3 +288,34 @@ def test_graphs_and_eager_agree_and_launches_are_counted():
     assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < 1e-5
     assert _lib.launch_count() - before > 30
     clear_plans()
+
+
+@pytest.mark.parametrize("name,kind,alpha", [
+    ("forest_lobpcg", "forest", lambda k: np.exp(-4 * k - 2)),
+    ("usps_lobpcg", "usps", lambda k: np.exp(-4 * k)),
+])
+def test_kfac_preconditioned_variant_matches_reference_golden(name, kind, alpha, tmp_path):
+    """params/usps_CNN_lobpcg.py / forest_lobpcg.py: lobpcg=True, kfac_rand=False (opt.py:426-430,491-493)."""
+    from optwboundeigenval_b200.spectral import SpectralState
+    from oracle import autograd_oracle as ao
+    g = load_golden(name)
+    meta = eval(str(g["meta"]))
+    model, loss = model_from_golden(kind, g)
+    st = SpectralState(model, loss, pow_iter_eps=meta["eps"], max_pow_iter=meta["max_pow_iter"], ignore_bad_vals=False,
+                       lobpcg=True, kfac_batch=meta["kfac_batch"], kfac_rand=False, pow_iter_alpha=alpha,
+                       verbose=True, verbose_log_file=str(tmp_path / "v.log"), log_file=str(tmp_path / "l.log"))
+    data = [torch.from_numpy(g["x"]), torch.from_numpy(g["y"])]
+    i, rn, size = st.comp_rho(data)
+    assert i == int(g["rho1_iters"])
+    assert abs(st.rho - float(g["rho1_rho"])) <= RTOL_LAM * float(g["rho1_rho"])
+    v = st.v.cpu().numpy()
+    assert min(rel_err(v, g["rho1_v"]), rel_err(-v, g["rho1_v"])) < 1e-3
+    # the preconditioner map itself against the CPU restatement of opt.py:384-416
+    cpu_model, _ = model_from_golden(kind, g)
+    pre = ao.KfacPreconditioner(cpu_model)
+    pre.build(data, loss)
+    gen = torch.Generator().manual_seed(1)
+    r = torch.randn(st.ndim, generator=gen, dtype=torch.float64)
+    want = pre.apply(r)
+    got = st.kfac(r)
+    assert rel_err(got.cpu().numpy(), want.numpy()) < 1e-4
