@@ -88,6 +88,11 @@ const char* b2s_last_error(void);
 /* number of kernels this library has launched (or captured graph kernel nodes replayed) since load */
 int64_t b2s_launch_count(void);
 
+/* Which contractions run on the tcgen05 / TMEM tensor-core path (3xTF32, fp32-accurate): 0 = none
+ * (CUDA-core kernels only), 1 = automatic (default: layers with >= 64 destination channels), 2 = every
+ * legal shape (tests).  Process-wide; set it before plans capture their graphs. */
+int b2s_set_tensor_core_mode(int32_t mode);
+
 /* ---- plan -------------------------------------------------------------------------- */
 /* Compiles a tape into an execution plan and allocates its workspaces (value, tangent
  * and adjoint caches for `max_batch` samples).  buf_elems[b] = elements per sample of

@@ -35,6 +35,7 @@ SIGNATURES = {
     "b2s_abi_version": (c_int32, []),
     "b2s_last_error": (c_char_p, []),
     "b2s_launch_count": (c_int64, []),
+    "b2s_set_tensor_core_mode": (c_int32, [c_int32]),
     "b2s_plan_create": (c_int32, [POINTER(CTensor), c_int32, POINTER(c_int64), c_int32, POINTER(COp), c_int32,
                                   c_int32, c_int32, c_int64, c_int32, c_int32, POINTER(c_void_p)]),
     "b2s_plan_destroy": (c_int32, [c_void_p]),

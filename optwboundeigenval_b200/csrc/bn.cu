@@ -10,10 +10,13 @@
 //
 // Two kernels per direction: a per-channel reduction (grid = C x splits, fp64 atomics) and an
 // elementwise apply (grid = C x chunks).  Both are HBM/L2-bandwidth bound.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 
 namespace b2s {
 
+namespace cg = cooperative_groups;
 
 template <int K>
 struct BnChan {
@@ -75,7 +78,7 @@ static inline dim3 bn_grid(const BnArgs& a) {
 
 // ---- forward statistics --------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) {
+__device__ __forceinline__ void bn_fwd_stats_body(const BnArgs& a) {
     __shared__ double red[64];
     const int c = blockIdx.x;
     const long long total = (long long)a.batch * a.HW;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) {
 
 // ---- forward apply -------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) {
+__device__ __forceinline__ void bn_fwd_apply_body(const BnArgs& a) {
     __shared__ BnChanRaw sch;
     const int c = blockIdx.x;
     if (threadIdx.x == 0) {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) {
 
 // ---- backward statistics: G_K = sum g_K, X_K = sum (g*xh)_K ----------------------------------
 template <int K>
-__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) {
+__device__ __forceinline__ void bn_bwd_stats_body(const BnArgs& a) {
     __shared__ double red[64];
     __shared__ BnChanRaw sch;
     const int c = blockIdx.x;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) {
 
 // ---- backward apply: xbar_K and the parameter-gradient slices ----------------------------------
 template <int K>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float pgrad_scale) {
+__device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_scale) {
     __shared__ BnChanRaw sch;
     __shared__ float sm[2][3];
     const int c = blockIdx.x;
@@ -233,6 +236,91 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float
         if (a.accumulate) out += a.xbar[ii];
         a.xbar[ii] = out;
     }
+}
+
+
+template <int K> __global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) { bn_fwd_stats_body<K>(a); }
+template <int K> __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) { bn_fwd_apply_body<K>(a); }
+template <int K> __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) { bn_bwd_stats_body<K>(a); }
+template <int K> __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float ps) { bn_bwd_apply_body<K>(a, ps); }
+
+// statistics + apply in ONE cooperative launch (grid-wide barrier between the two phases): halves the
+// number of dependent launches on the critical path of a pass; used when no cross-GPU reduction has to
+// happen between the phases.
+template <int K>
+__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnArgs a, int do_stats) {
+    if (do_stats) bn_fwd_stats_body<K>(a);
+    __threadfence();
+    cg::this_grid().sync();
+    bn_fwd_apply_body<K>(a);
+}
+template <int K>
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float ps) {
+    bn_bwd_stats_body<K>(a);
+    __threadfence();
+    cg::this_grid().sync();
+    bn_bwd_apply_body<K>(a, ps);
+}
+
+template <typename F>
+static dim3 coop_grid(const BnArgs& a, F kernel) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
+    if (per_sm < 1) per_sm = 1;
+    dim3 g = bn_grid(a);
+    const long long cap = (long long)per_sm * kNumSMs;
+    long long splits = g.y;
+    if ((long long)g.x * splits > cap) splits = cap / g.x;
+    if (splits < 1) splits = 1;
+    return dim3(g.x, (unsigned)splits);
+}
+
+template <int K>
+static int launch_fwd_fused_t(cudaStream_t st, const BnArgs& a, int do_stats) {
+    const dim3 grid = coop_grid(a, bn_fwd_fused_kernel<K>);
+    if ((long long)grid.x * grid.y > (long long)kNumSMs * 4) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_fwd_fused_kernel<K>, 256, 0);
+        if ((long long)grid.x * grid.y > (long long)per_sm * kNumSMs) return 1;   // cannot be co-resident
+    }
+    BnArgs args = a;
+    void* params[] = {(void*)&args, (void*)&do_stats};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_kernel<K>, grid, dim3(256), params, 0, st);
+    if (e != cudaSuccess) { set_error("cooperative BN launch: %s", cudaGetErrorString(e)); return -3; }
+    count_launch();
+    return 0;
+}
+template <int K>
+static int launch_bwd_fused_t(cudaStream_t st, const BnArgs& a) {
+    const dim3 grid = coop_grid(a, bn_bwd_fused_kernel<K>);
+    if ((long long)grid.x * grid.y > (long long)kNumSMs * 4) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<K>, 256, 0);
+        if ((long long)grid.x * grid.y > (long long)per_sm * kNumSMs) return 1;
+    }
+    BnArgs args = a;
+    float ps = a.pgrad_scale;
+    void* params[] = {(void*)&args, (void*)&ps};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<K>, grid, dim3(256), params, 0, st);
+    if (e != cudaSuccess) { set_error("cooperative BN launch: %s", cudaGetErrorString(e)); return -3; }
+    count_launch();
+    return 0;
+}
+
+// returns 0 on success, 1 when the fused form does not apply (caller uses the two-kernel form), <0 on error
+int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stats) {
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_fwd_fused", 16.0 * elems, 4.0 * elems * (2 * order + 3), st);
+    if (order == 0) return launch_fwd_fused_t<0>(st, a, do_stats);
+    if (order == 1) return launch_fwd_fused_t<1>(st, a, do_stats);
+    return launch_fwd_fused_t<2>(st, a, do_stats);
+}
+int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_bwd_fused", 16.0 * elems, 4.0 * elems * (4 * order + 7), st);
+    if (order == 0) return launch_bwd_fused_t<0>(st, a);
+    if (order == 1) return launch_bwd_fused_t<1>(st, a);
+    return launch_bwd_fused_t<2>(st, a);
 }
 
 int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a) {

@@ -14,25 +14,12 @@
 // single-pass TF32).  GEMM view:
 //   forward / dgrad:  M = destination channels, N = batch*pixels, K = source channels*KH*KW
 //   wgrad:            M = Cout, N = Cin*KH*KW, K = batch*pixels (split across blockIdx.z)
+#include "conv_args.h"
 #include "kernels.h"
 
 namespace b2s {
 
-struct ConvKArgs {
-    ConvGeom g;
-    const float* act[kMaxPairs];   // gather source (forward: x-like; dgrad: ybar-like; wgrad: x-like)
-    const float* wt[kMaxPairs];    // weights (forward/dgrad) or adjoint (wgrad)
-    float scale[kMaxPairs];
-    int npairs;
-    const float* bias;
-    const float* relu_ref;
-    int relu_mode;
-    float* out;
-    int accumulate;
-    int k_chunk;                   // wgrad: K elements per blockIdx.z
-};
-
-enum { MODE_FWD = 0, MODE_DGRAD = 1 };
+// ConvKArgs / MODE_* live in conv_args.h (shared with the tcgen05 path, conv_tc.cu)
 
 // ---------------------------------------------------------------------------------------------
 // forward / dgrad
@@ -205,7 +192,7 @@ conv_px_kernel(const ConvKArgs a, const int groups, const int slices, const int 
     const long long J = (long long)g.batch * HWd;
     const int Mpad = groups * MT;
     float* Wsm = px_smem;                       // [Ktot][Mpad]
-    float* red = px_smem + (size_t)Ktot * Mpad; // [pw_count][Mpad][32]
+    float* red = px_smem + (size_t)Ktot * Mpad; // [slices][pw_count][Mpad][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pw = warp % pw_count;
@@ -248,14 +235,20 @@ conv_px_kernel(const ConvKArgs a, const int groups, const int slices, const int 
         __syncthreads();
         const float* __restrict__ wt = a.wt[p];
         const float sc = a.scale[p];
-        for (int idx = tid; idx < Ktot * Mpad; idx += blockDim.x) {
-            const int k = idx / Mpad, m = idx - k * Mpad;
-            float v = 0.f;
-            if (m < Cd) {
-                if (MODE == MODE_FWD) v = wt[(long long)m * Ktot + k];
-                else { const int c = k / KHW, t = k - c * KHW; v = wt[((long long)c * g.Cin + m) * KHW + t]; }
+        if (MODE == MODE_FWD) {
+            // global layout [m][k]: consecutive threads read consecutive k (coalesced), scatter into [k][m]
+            for (int idx = tid; idx < Ktot * Mpad; idx += blockDim.x) {
+                const int m = idx / Ktot, k = idx - m * Ktot;
+                Wsm[(size_t)k * Mpad + m] = m < Cd ? wt[(long long)m * Ktot + k] * sc : 0.f;
             }
-            Wsm[idx] = v * sc;
+        } else {
+            // global layout [c][m][t] (c = conv output channel): read contiguous runs of (m,t)
+            const int MK = Mpad * KHW;
+            for (int idx = tid; idx < Cs * MK; idx += blockDim.x) {
+                const int c = idx / MK, r = idx - c * MK;
+                const int m = r / KHW, t = r - m * KHW;
+                Wsm[((size_t)c * KHW + t) * Mpad + m] = m < Cd ? wt[((long long)c * g.Cin + m) * KHW + t] * sc : 0.f;
+            }
         }
         __syncthreads();
         const float* __restrict__ src = a.act[p] + (long long)n * s_ss;
@@ -305,28 +298,24 @@ conv_px_kernel(const ConvKArgs a, const int groups, const int slices, const int 
             }
         }
     }
-    // ---- sum the K slices (fixed order: deterministic) -------------------------------------------
+    // ---- sum the K slices: every slice parks its partials, then slice `sl` of each (pixel warp, group)
+    // adds up channels mm = sl, sl+slices, ... over all slices in fixed order (deterministic)
+    const size_t slice_stride = (size_t)pw_count * Mpad * 32;
     float* myred = red + ((size_t)pw * Mpad + gi * MT) * 32 + lane;
-    for (int r = 0; r < slices; ++r) {
-        if (sl == r) {
-            if (r == 0) {
+    {
+        float* dst = myred + (size_t)sl * slice_stride;
 #pragma unroll
-                for (int m = 0; m < MT; ++m) myred[m * 32] = acc[m];
-            } else {
-#pragma unroll
-                for (int m = 0; m < MT; ++m) myred[m * 32] += acc[m];
-            }
-        }
-        __syncthreads();
+        for (int m = 0; m < MT; ++m) dst[m * 32] = acc[m];
     }
-    // ---- epilogue: slice `sl` of each (pixel warp, group) writes channels mm = sl, sl+slices, ...
+    __syncthreads();
     if (!ok) return;
     const long long base = (long long)n * d_ss + pix;
     for (int mm = sl; mm < MT; mm += slices) {
         const int m = gi * MT + mm;
         if (m >= Cd) break;
         const long long o = base + (long long)m * HWd;
-        float v = myred[mm * 32];
+        float v = 0.f;
+        for (int r = 0; r < slices; ++r) v += myred[(size_t)r * slice_stride + mm * 32];
         if (a.bias) v += a.bias[m];
         if (a.accumulate) v += a.out[o];
         if (a.relu_mode == 1) v = v > 0.f ? v : 0.f;
@@ -379,7 +368,11 @@ static bool try_launch_px(cudaStream_t st, const ConvKArgs& a) {
     int slices = 16 / (pw * groups);
     if (slices > Cs) slices = Cs;
     if (slices < 1) slices = 1;
-    const size_t smem = wbytes + (size_t)pw * best_pad * 32 * sizeof(float);
+    size_t smem = wbytes + (size_t)slices * pw * best_pad * 32 * sizeof(float);
+    while (smem > 200 * 1024 && slices > 1) {
+        slices >>= 1;
+        smem = wbytes + (size_t)slices * pw * best_pad * 32 * sizeof(float);
+    }
     if (smem > 200 * 1024) return false;
     const int blocks = (int)((J + 32 * pw - 1) / (32 * pw));
     switch (MT) {
@@ -541,6 +534,14 @@ static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
     const double io = 4.0 * ((double)g.batch * g.Cin * g.H * g.W * a.npairs + (double)g.batch * g.Cout * g.OH * g.OW +
                              (double)g.Cout * g.Cin * g.KH * g.KW * a.npairs);
     ProfScope prof(MODE == MODE_FWD ? "conv_fwd" : "conv_dgrad", 2.0 * macs * a.npairs, io, st);
+    {
+        const int rc = try_launch_conv_tc(MODE, st, a);      // tcgen05 path for wide layers
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            B2S_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (try_launch_px<MODE>(st, a)) {
         B2S_LAUNCH_CHECK();
         return 0;

@@ -84,6 +84,9 @@ int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_bwd_apply(cudaStream_t st, int order, const BnArgs& a);
+// fused statistics+apply (cooperative launch); return 1 = not applicable, use the two-kernel form
+int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stats);
+int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a);
 // reference-compatible third order (see bn.cu): first-order sweep with the dropped adjoint injected
 int bn_corr_sums();
 int launch_bn_corr_stats(cudaStream_t st, const BnArgs& a, const float* gc);

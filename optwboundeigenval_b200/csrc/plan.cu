@@ -20,6 +20,7 @@
 
 #include "../../include/b200_spectral.h"
 #include "comm.h"
+#include "conv_args.h"
 #include "kernels.h"
 #include "vec.h"
 
@@ -98,7 +99,9 @@ struct b2s_plan {
     int device = 0;
     cudaStream_t caller = nullptr;    // stream the caller's tensors are ordered on
     cudaStream_t stream = nullptr;    // plan-owned work stream (graphs cannot be captured on stream 0)
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaStream_t side = nullptr;      // weight-gradient contractions run here, off the adjoint critical path
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    bool side_used = false;
     bool use_graphs = true;
     std::vector<b2s_tensor> tensors;
     std::vector<b2s_op> ops;
@@ -128,6 +131,7 @@ struct b2s_plan {
     double* csum = nullptr;           // sums of the third-order compatibility sweep
     float* out_corr = nullptr;        // its parameter-space result
     bool bn_exact_third_order = false;
+    bool bn_fused = true;             // statistics+apply in one cooperative launch (single GPU)
     std::vector<float*> bn_rm, bn_rv;
 
     // max pool
@@ -271,11 +275,17 @@ static int forward(b2s_plan* p, int K) {
         }
         case B2S_OP_BN: {
             const BnArgs a = bn_args(p, (int)oi, K);
-            if (!(first && K > 0)) {
-                B2S_TRY(launch_bn_fwd_stats(st, K, a));
-                if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.fsum[K], 2 * a.C, st));
+            const int do_stats = !(first && K > 0);
+            int rc = 1;
+            if (!p->comm && p->bn_fused) rc = launch_bn_fwd_fused(st, K, a, do_stats);
+            if (rc < 0) return rc;
+            if (rc == 1) {
+                if (do_stats) {
+                    B2S_TRY(launch_bn_fwd_stats(st, K, a));
+                    if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.fsum[K], 2 * a.C, st));
+                }
+                B2S_TRY(launch_bn_fwd_apply(st, K, a));
             }
-            B2S_TRY(launch_bn_fwd_apply(st, K, a));
             break;
         }
         case B2S_OP_RELU:
@@ -314,6 +324,23 @@ static int forward(b2s_plan* p, int K) {
     return 0;
 }
 
+// The weight/bias gradient of a layer is a leaf of the backward sweep: nothing downstream reads it
+// before the pass ends.  Fork it onto the side stream (ordered after everything enqueued so far on
+// the main stream) so the adjoint chain  dgrad -> BN backward -> dgrad ...  does not wait for it.
+static int fork_side(b2s_plan* p) {
+    B2S_CUDA(cudaEventRecord(p->ev_fork, p->stream));
+    B2S_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    p->side_used = true;
+    return 0;
+}
+static int join_side(b2s_plan* p) {
+    if (!p->side_used) return 0;
+    B2S_CUDA(cudaEventRecord(p->ev_join, p->side));
+    B2S_CUDA(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+    p->side_used = false;
+    return 0;
+}
+
 // ---- backward sweep of order K ----------------------------------------------------------------
 static int backward(b2s_plan* p, int K) {
     cudaStream_t st = p->stream;
@@ -344,9 +371,10 @@ static int backward(b2s_plan* p, int K) {
             a_[np] = x[0]; b_[np] = gk[K]; sc[np] = 1.f; ++np;
             if (!first && K >= 1) { a_[np] = x[1]; b_[np] = gk[K - 1]; sc[np] = K == 2 ? 2.f : 1.f; ++np; }
             if (!first && K == 2) { a_[np] = x[2]; b_[np] = gk[0]; sc[np] = 1.f; ++np; }
-            B2S_TRY(launch_conv_wgrad(st, g, np, a_, b_, sc, p->out32[K] + op.w_off));
+            B2S_TRY(fork_side(p));
+            B2S_TRY(launch_conv_wgrad(p->side, g, np, a_, b_, sc, p->out32[K] + op.w_off));
             if (op.b_off >= 0)
-                B2S_TRY(launch_bias_grad(st, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
+                B2S_TRY(launch_bias_grad(p->side, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
                                          p->out32[K] + op.b_off));
             if (!first) {
                 np = 0;
@@ -358,9 +386,14 @@ static int backward(b2s_plan* p, int K) {
         }
         case B2S_OP_BN: {
             const BnArgs a = bn_args(p, oi, K);
-            B2S_TRY(launch_bn_bwd_stats(st, K, a));
-            if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.bsum[K], 2 * a.C, st));
-            B2S_TRY(launch_bn_bwd_apply(st, K, a));
+            int rc = 1;
+            if (!p->comm && p->bn_fused) rc = launch_bn_bwd_fused(st, K, a);
+            if (rc < 0) return rc;
+            if (rc == 1) {
+                B2S_TRY(launch_bn_bwd_stats(st, K, a));
+                if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.bsum[K], 2 * a.C, st));
+                B2S_TRY(launch_bn_bwd_apply(st, K, a));
+            }
             break;
         }
         case B2S_OP_RELU:
@@ -389,6 +422,7 @@ static int backward(b2s_plan* p, int K) {
             return -5;
         }
     }
+    B2S_TRY(join_side(p));
     if (p->comm) B2S_TRY(comm_allreduce_f32(p->comm, p->out32[K], p->P, st));
     return 0;
 }
@@ -415,9 +449,10 @@ static int backward_correction(b2s_plan* p) {
             const float* gc = tptr(p, p->bw, 2, op.out);
             const float* W = p->params + op.w_off;
             const float one = 1.f;
-            B2S_TRY(launch_conv_wgrad(st, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
+            B2S_TRY(fork_side(p));
+            B2S_TRY(launch_conv_wgrad(p->side, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
             if (op.b_off >= 0)
-                B2S_TRY(launch_bias_grad(st, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
+                B2S_TRY(launch_bias_grad(p->side, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
             if (!first) B2S_TRY(launch_conv_dgrad(st, g, 1, &gc, &W, &one, tptr(p, p->bw, 2, op.in), acc));
             break;
         }
@@ -458,6 +493,7 @@ static int backward_correction(b2s_plan* p) {
             return -5;
         }
     }
+    B2S_TRY(join_side(p));
     if (p->comm) B2S_TRY(comm_allreduce_f32(p->comm, p->out_corr, p->P, st));
     return 0;
 }
@@ -657,6 +693,9 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     int rc = 0;
     auto fail = [&](int code) { b2s_plan_destroy(p); return code; };
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess) {
         set_error("b2s_plan_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -711,6 +750,9 @@ int b2s_plan_destroy(b2s_plan* p) {
     cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
     if (p->pi) b2s_pi_destroy(p->pi);
     if (p->comm) comm_destroy(p->comm);
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->ev_out) cudaEventDestroy(p->ev_out);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -725,10 +767,16 @@ int b2s_plan_set_stream(b2s_plan* p, void* cuda_stream) {
 }
 int b2s_plan_set_graphs(b2s_plan* p, int32_t use_graphs) {
     if (!p) return -1;
-    p->use_graphs = use_graphs != 0;
+    p->use_graphs = (use_graphs & 1) != 0;
+    p->bn_fused = (use_graphs & 2) == 0;       // bit 1: disable the cooperative BatchNorm kernels (debug)
     return 0;
 }
 int64_t b2s_plan_workspace_bytes(const b2s_plan* p) { return p ? p->workspace : 0; }
+int b2s_set_tensor_core_mode(int32_t mode) {
+    if (mode < 0 || mode > 2) { set_error("b2s_set_tensor_core_mode: mode must be 0, 1 or 2"); return -1; }
+    set_tc_mode(mode);
+    return 0;
+}
 int b2s_plan_set_bn_third_order(b2s_plan* p, int32_t exact) {
     if (!p) return -1;
     p->bn_exact_third_order = exact != 0;
@@ -843,6 +891,8 @@ int b2s_debug_read(b2s_plan* p, int32_t adjoint, int32_t order, int32_t tensor, 
 }
 
 int b2s_profile_pass(b2s_plan* p, int32_t order, int32_t reps, b2s_prof_entry* out, int32_t cap, int32_t* n_out) {
+    const bool raw = (order & 0x100) != 0;       // one entry per launch, in launch order
+    order &= 0xff;
     if (!p || !out || !n_out || order < 0 || order > 3 || reps <= 0) { set_error("b2s_profile_pass: invalid arguments"); return -1; }
     if (p->batch <= 0) { set_error("b2s_profile_pass: call b2s_base_pass first"); return -1; }
     if (order == 3 && !p->out_corr) { set_error("b2s_profile_pass: run b2s_vghv once before profiling the compatibility sweep"); return -1; }
@@ -859,17 +909,23 @@ int b2s_profile_pass(b2s_plan* p, int32_t order, int32_t reps, b2s_prof_entry* o
     cudaStreamSynchronize(p->stream);
     std::map<std::string, b2s_prof_entry> agg;
     std::vector<std::string> order_seen;
+    const size_t per_pass = prof.recs.size() / (size_t)reps;
+    size_t ri = 0;
     for (auto& r : prof.recs) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
-        auto it = agg.find(r.name);
+        char key[64];
+        if (raw) snprintf(key, sizeof(key), "%s#%03d", r.name, (int)(per_pass ? ri % per_pass : ri));
+        else snprintf(key, sizeof(key), "%s", r.name);
+        ++ri;
+        auto it = agg.find(key);
         if (it == agg.end()) {
             b2s_prof_entry e{};
-            snprintf(e.name, sizeof(e.name), "%s", r.name);
-            it = agg.emplace(r.name, e).first;
-            order_seen.push_back(r.name);
+            snprintf(e.name, sizeof(e.name), "%s", key);
+            it = agg.emplace(key, e).first;
+            order_seen.push_back(key);
         }
         it->second.launches += 1;
         it->second.ms += ms;

@@ -192,14 +192,15 @@ class SpectralPlan:
         """False (default): reproduce nested torch.autograd's third-order BatchNorm result; True: exact."""
         _lib.check(self.lib.b2s_plan_set_bn_third_order(self.handle, 1 if exact else 0))
 
-    def profile(self, order: int, reps: int = 3):
+    def profile(self, order: int, reps: int = 3, raw: bool = False):
         """Per kernel family: launches / ms / algorithmic FLOPs and bytes of one pass (CUDA events on the
         launching stream around every kernel)."""
         self._bind_stream()
-        cap = 64
+        cap = 4096 if raw else 64
         arr = (_lib.ProfEntry * cap)()
         n = ctypes.c_int32(0)
-        _lib.check(self.lib.b2s_profile_pass(self.handle, order, reps, arr, cap, ctypes.byref(n)), "b2s_profile_pass")
+        _lib.check(self.lib.b2s_profile_pass(self.handle, order | (0x100 if raw else 0), reps, arr, cap,
+                                             ctypes.byref(n)), "b2s_profile_pass")
         return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, flops=arr[i].flops,
                      bytes=arr[i].bytes) for i in range(n.value)]
 

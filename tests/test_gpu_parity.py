@@ -319,3 +319,58 @@ def test_kfac_preconditioned_variant_matches_reference_golden(name, kind, alpha,
     want = pre.apply(r)
     got = st.kfac(r)
     assert rel_err(got.cpu().numpy(), want.numpy()) < 1e-4
+
+
+def test_tensor_core_path_matches_cuda_core_path_and_oracle():
+    """tcgen05 / TMEM 3xTF32 contractions (conv_tc.cu) against the fp32 CUDA-core kernels and the CPU oracle on
+    a network with wide layers: 3x3 and 1x1 convs with and without bias, ragged channel counts, a pixel count
+    that is not a multiple of the 128-row tile."""
+    import torch.nn as nn
+    from optwboundeigenval_b200 import _lib
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator, clear_plans
+    from oracle import autograd_oracle as ao
+    torch.manual_seed(5)
+
+    class Wide(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1 = nn.Conv2d(5, 72, 3, padding=1)
+            self.c2 = nn.Conv2d(72, 136, 3, padding=1, bias=False)
+            self.bn = nn.BatchNorm2d(136)
+            self.c3 = nn.Conv2d(136, 64, 1)
+            self.pool = nn.MaxPool2d(2)
+            self.fc = nn.Linear(64 * 5 * 5, 7)
+
+        def forward(self, x):
+            h = torch.relu(self.c1(x))
+            h = torch.relu(self.bn(self.c2(h)))
+            h = self.pool(torch.relu(self.c3(h)))
+            return self.fc(h.view(-1, 64 * 25))
+
+    model = Wide().train()
+    loss = nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(6, 5, 10, 10, generator=g)          # 600 pixels: 4 full tiles + a ragged one
+    y = torch.randint(0, 7, (6,), generator=g)
+    P = sum(p.numel() for p in model.parameters())
+    v = torch.randn(P, generator=g, dtype=torch.float64)
+    v /= v.norm()
+    ref = ao.AutogradSpectralOperator(copy.deepcopy(model), [x, y], loss)
+    lib = _lib.load()
+    res = {}
+    try:
+        for mode in (0, 2):
+            clear_plans()
+            _lib.check(lib.b2s_set_tensor_core_mode(mode))
+            op = B200HVPOperator(model, [x, y], loss)
+            hv = op.Hv(v, storedGrad=True)
+            vg = op.vGHv(v, storedGrad=True)
+            res[mode] = (op.stored_grad.cpu().numpy(), hv.cpu().numpy(), vg.cpu().numpy())
+    finally:
+        _lib.check(lib.b2s_set_tensor_core_mode(1))
+        clear_plans()
+    for a, b in zip(res[2], res[0]):
+        assert rel_err(a, b) < 2e-5
+    assert rel_err(res[2][0], ref.gradient().detach().numpy()) < RTOL_VEC
+    assert rel_err(res[2][1], ref.hv(v).numpy()) < RTOL_VEC
+    assert rel_err(res[2][2], ref.vghv(v).numpy()) < RTOL_VEC

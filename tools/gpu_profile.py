@@ -38,6 +38,13 @@ def main():
             gb = r["bytes"] / r["ms"] / 1e6 if r["ms"] > 0 else 0
             print("   %-16s launches %4d  %8.3f ms (%5.1f%%)  %9.2f TFLOP/s  %8.1f GB/s" % (
                 r["name"], r["launches"], r["ms"], 100 * r["ms"] / tot, gf, gb))
+    if os.environ.get("PROF_RAW", "0") == "1":
+        rows = op.plan.profile(1, reps=3, raw=True)
+        tape = op.plan.tape
+        print("--- raw per-launch timeline of the Hv pass (us)")
+        for r in rows:
+            print("   %-24s %8.1f us  %8.2f TFLOP/s %8.1f GB/s" % (r["name"], r["ms"] * 1e3,
+                  r["flops"] / r["ms"] / 1e9 if r["ms"] > 0 else 0, r["bytes"] / r["ms"] / 1e6 if r["ms"] > 0 else 0))
     # wall clock of the graph-replayed HVP
     for _ in range(3):
         op.plan.hv(v)
