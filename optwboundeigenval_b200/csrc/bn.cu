@@ -58,17 +58,69 @@ __device__ inline BnChan<K> bn_channel(const BnArgs& a, int c) {
     return ch;
 }
 
-template <int K>
-__device__ __forceinline__ Jet<K, float> load_jet(const float* const* p, long long idx) {
-    Jet<K, float> j;
-    j.c[0] = p[0][idx];
-    if (K >= 1) j.c[1] = p[1] ? p[1][idx] : 0.f;
-    if (K >= 2) j.c[2] = p[2] ? p[2][idx] : 0.f;
+// ---- element iteration ----------------------------------------------------------------------
+// A channel's elements are the (sample, pixel) pairs of one NCHW plane per sample.  Threads walk them in
+// chunks of VEC consecutive pixels (VEC = 4: 128-bit loads/stores when the plane size and all strides
+// are multiples of 4 floats and the bases are 16-byte aligned; VEC = 1 otherwise).  Index arithmetic
+// is 32-bit (one unsigned division per chunk, none per element).
+template <int VEC>
+struct Pack {
+    float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> ld_pack(const float* __restrict__ p, long long idx) {
+    Pack<VEC> r;
+    if (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p + idx);
+        r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w;
+    } else {
+        r.v[0] = p[idx];
+    }
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> zero_pack() {
+    Pack<VEC> r;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) r.v[e] = 0.f;
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_pack(float* __restrict__ p, long long idx, const Pack<VEC>& r) {
+    if (VEC == 4) *reinterpret_cast<float4*>(p + idx) = make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]);
+    else p[idx] = r.v[0];
+}
+// jets of VEC consecutive elements, components above K untouched
+template <int K, int VEC>
+struct JetPack {
+    Pack<VEC> c[3];
+    __device__ __forceinline__ Jet<K, float> at(int e) const {
+        return Jet<K, float>(c[0].v[e], K >= 1 ? c[1].v[e] : 0.f, K >= 2 ? c[2].v[e] : 0.f);
+    }
+};
+template <int K, int VEC>
+__device__ __forceinline__ JetPack<K, VEC> load_jets(const float* const* p, long long idx) {
+    JetPack<K, VEC> j;
+    j.c[0] = ld_pack<VEC>(p[0], idx);
+    if (K >= 1) j.c[1] = p[1] ? ld_pack<VEC>(p[1], idx) : zero_pack<VEC>();
+    if (K >= 2) j.c[2] = p[2] ? ld_pack<VEC>(p[2], idx) : zero_pack<VEC>();
     return j;
 }
 
-static inline dim3 bn_grid(const BnArgs& a) {
-    const long long total = (long long)a.batch * a.HW;
+template <int VEC, typename F>
+__device__ __forceinline__ void bn_foreach(const BnArgs& a, int c, F&& f) {
+    const unsigned Q = (unsigned)(a.HW / VEC);
+    const unsigned total = (unsigned)a.batch * Q;
+    const long long coff = (long long)c * a.HW;
+    for (unsigned i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+        const unsigned n = i / Q, q = i - n * Q;
+        const long long off = coff + (long long)q * VEC;
+        f((long long)n * a.in_sstride + off, (long long)n * a.out_sstride + off);
+    }
+}
+
+static inline dim3 bn_grid(const BnArgs& a, int vec) {
+    const long long total = (long long)a.batch * a.HW / vec;
     long long splits = (total + 256 * 2 - 1) / (256 * 2);
     long long cap = (8LL * kNumSMs + a.C - 1) / a.C;
     if (splits > cap) splits = cap;
@@ -76,37 +128,49 @@ static inline dim3 bn_grid(const BnArgs& a) {
     return dim3((unsigned)a.C, (unsigned)splits);
 }
 
+// 128-bit path is legal when every plane starts 16-byte aligned
+static inline int bn_vec(const BnArgs& a, const float* extra = nullptr) {
+    if (a.HW % 4 != 0 || a.in_sstride % 4 != 0 || a.out_sstride % 4 != 0) return 1;
+    auto ok = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+    for (int k = 0; k < 3; ++k)
+        if (!ok(a.x[k]) || !ok(a.g[k])) return 1;
+    if (!ok(a.y0) || !ok(a.yk) || !ok(a.xbar) || !ok(extra)) return 1;
+    return 4;
+}
+
 // ---- forward statistics --------------------------------------------------------------------
-template <int K>
+template <int K, int VEC>
 __device__ __forceinline__ void bn_fwd_stats_body(const BnArgs& a) {
     __shared__ double red[64];
     const int c = blockIdx.x;
-    const long long total = (long long)a.batch * a.HW;
     const double N = (double)a.count;
     float mu0 = 0.f, mu1 = 0.f;
     if (K >= 1) mu0 = (float)(a.fsum[0][0 * a.C + c] / N);
     if (K >= 2) mu1 = (float)(a.fsum[1][0 * a.C + c] / N);
     double T = 0, Q = 0;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.y * blockDim.x) {
-        const int n = (int)(i / a.HW);
-        const int pix = (int)(i - (long long)n * a.HW);
-        const long long idx = (long long)n * a.in_sstride + (long long)c * a.HW + pix;
-        if (K == 0) {
-            const float x0 = a.x[0][idx];
-            T += x0;
-            Q += (double)x0 * x0;
-        } else if (K == 1) {
-            const float x0 = a.x[0][idx], x1 = a.x[1][idx];
-            T += x1;
-            Q += 2.0 * (double)((x0 - mu0) * x1);
-        } else {
-            const float x0 = a.x[0][idx], x1 = a.x[1][idx], x2 = a.x[2][idx];
-            const float c1 = x1 - mu1;
-            T += x2;
-            Q += 2.0 * (double)(c1 * c1 + (x0 - mu0) * x2);
+    bn_foreach<VEC>(a, c, [&](long long ii, long long oi) {
+        (void)oi;
+        const JetPack<K, VEC> x = load_jets<K, VEC>(a.x, ii);
+        float t = 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float x0 = x.c[0].v[e];
+            if (K == 0) {
+                t += x0;
+                Q += (double)x0 * x0;
+            } else if (K == 1) {
+                const float x1 = x.c[1].v[e];
+                t += x1;
+                Q += 2.0 * (double)((x0 - mu0) * x1);
+            } else {
+                const float x1 = x.c[1].v[e], x2 = x.c[2].v[e];
+                const float c1 = x1 - mu1;
+                t += x2;
+                Q += 2.0 * (double)(c1 * c1 + (x0 - mu0) * x2);
+            }
         }
-    }
+        T += (double)t;
+    });
     double v[2] = {T, Q};
     block_sum<2, double>(v, red);
     if (threadIdx.x == 0) {
@@ -116,7 +180,7 @@ __device__ __forceinline__ void bn_fwd_stats_body(const BnArgs& a) {
 }
 
 // ---- forward apply -------------------------------------------------------------------------
-template <int K>
+template <int K, int VEC>
 __device__ __forceinline__ void bn_fwd_apply_body(const BnArgs& a) {
     __shared__ BnChanRaw sch;
     const int c = blockIdx.x;
@@ -135,28 +199,28 @@ __device__ __forceinline__ void bn_fwd_apply_body(const BnArgs& a) {
     }
     __syncthreads();
     const BnChan<K> ch = from_raw<K>(sch);
-    const long long total = (long long)a.batch * a.HW;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.y * blockDim.x) {
-        const int n = (int)(i / a.HW);
-        const int pix = (int)(i - (long long)n * a.HW);
-        const long long off = (long long)c * a.HW + pix;
-        const long long ii = (long long)n * a.in_sstride + off;
-        const long long oi = (long long)n * a.out_sstride + off;
-        const Jet<K, float> x = load_jet<K>(a.x, ii);
-        const Jet<K, float> xh = (x - ch.mu) * ch.r;
-        const Jet<K, float> y = ch.gam * xh + ch.bet;
-        float out = y.c[K];
-        if (a.relu) {
-            if (K == 0) out = out > 0.f ? out : 0.f;
-            else out = a.y0[oi] > 0.f ? out : 0.f;
+    bn_foreach<VEC>(a, c, [&](long long ii, long long oi) {
+        const JetPack<K, VEC> x = load_jets<K, VEC>(a.x, ii);
+        Pack<VEC> y0 = zero_pack<VEC>();
+        if (a.relu && K > 0) y0 = ld_pack<VEC>(a.y0, oi);
+        Pack<VEC> out;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const Jet<K, float> xh = (x.at(e) - ch.mu) * ch.r;
+            const Jet<K, float> y = ch.gam * xh + ch.bet;
+            float o = y.c[K];
+            if (a.relu) {
+                if (K == 0) o = o > 0.f ? o : 0.f;
+                else o = y0.v[e] > 0.f ? o : 0.f;
+            }
+            out.v[e] = o;
         }
-        a.yk[oi] = out;
-    }
+        st_pack<VEC>(a.yk, oi, out);
+    });
 }
 
 // ---- backward statistics: G_K = sum g_K, X_K = sum (g*xh)_K ----------------------------------
-template <int K>
+template <int K, int VEC>
 __device__ __forceinline__ void bn_bwd_stats_body(const BnArgs& a) {
     __shared__ double red[64];
     __shared__ BnChanRaw sch;
@@ -164,22 +228,24 @@ __device__ __forceinline__ void bn_bwd_stats_body(const BnArgs& a) {
     if (threadIdx.x == 0) to_raw<K>(bn_channel<K>(a, c), sch);
     __syncthreads();
     const BnChan<K> ch = from_raw<K>(sch);
-    const long long total = (long long)a.batch * a.HW;
     double G = 0, X = 0;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.y * blockDim.x) {
-        const int n = (int)(i / a.HW);
-        const int pix = (int)(i - (long long)n * a.HW);
-        const long long off = (long long)c * a.HW + pix;
-        const long long ii = (long long)n * a.in_sstride + off;
-        const long long oi = (long long)n * a.out_sstride + off;
-        if (a.relu && !(a.y0[oi] > 0.f)) continue;
-        const Jet<K, float> x = load_jet<K>(a.x, ii);
-        const Jet<K, float> xh = (x - ch.mu) * ch.r;
-        const Jet<K, float> g = load_jet<K>(a.g, oi);
-        G += g.c[K];
-        X += (g * xh).c[K];
-    }
+    bn_foreach<VEC>(a, c, [&](long long ii, long long oi) {
+        const JetPack<K, VEC> x = load_jets<K, VEC>(a.x, ii);
+        const JetPack<K, VEC> g = load_jets<K, VEC>(a.g, oi);
+        Pack<VEC> y0 = zero_pack<VEC>();
+        if (a.relu) y0 = ld_pack<VEC>(a.y0, oi);
+        float gs = 0.f, xs = 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (a.relu && !(y0.v[e] > 0.f)) continue;
+            const Jet<K, float> xh = (x.at(e) - ch.mu) * ch.r;
+            const Jet<K, float> ge = g.at(e);
+            gs += ge.c[K];
+            xs += (ge * xh).c[K];
+        }
+        G += (double)gs;
+        X += (double)xs;
+    });
     double v[2] = {G, X};
     block_sum<2, double>(v, red);
     if (threadIdx.x == 0) {
@@ -189,7 +255,7 @@ __device__ __forceinline__ void bn_bwd_stats_body(const BnArgs& a) {
 }
 
 // ---- backward apply: xbar_K and the parameter-gradient slices ----------------------------------
-template <int K>
+template <int K, int VEC>
 __device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_scale) {
     __shared__ BnChanRaw sch;
     __shared__ float sm[2][3];
@@ -218,90 +284,99 @@ __device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_s
     Jet<K, float> m1, m2;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { m1.c[k] = sm[0][k]; m2.c[k] = sm[1][k]; }
-    const long long total = (long long)a.batch * a.HW;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.y * blockDim.x) {
-        const int n = (int)(i / a.HW);
-        const int pix = (int)(i - (long long)n * a.HW);
-        const long long off = (long long)c * a.HW + pix;
-        const long long ii = (long long)n * a.in_sstride + off;
-        const long long oi = (long long)n * a.out_sstride + off;
-        const Jet<K, float> x = load_jet<K>(a.x, ii);
-        const Jet<K, float> xh = (x - ch.mu) * ch.r;
-        Jet<K, float> g;
-        if (!a.relu || a.y0[oi] > 0.f) g = load_jet<K>(a.g, oi);
-        const Jet<K, float> u = ch.gam * g - m1 - xh * m2;
-        const Jet<K, float> xb = ch.r * u;
-        float out = xb.c[K];
-        if (a.accumulate) out += a.xbar[ii];
-        a.xbar[ii] = out;
-    }
+    bn_foreach<VEC>(a, c, [&](long long ii, long long oi) {
+        const JetPack<K, VEC> x = load_jets<K, VEC>(a.x, ii);
+        const JetPack<K, VEC> g = load_jets<K, VEC>(a.g, oi);
+        Pack<VEC> y0 = zero_pack<VEC>();
+        if (a.relu) y0 = ld_pack<VEC>(a.y0, oi);
+        Pack<VEC> out = zero_pack<VEC>();
+        if (a.accumulate) out = ld_pack<VEC>(a.xbar, ii);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const Jet<K, float> xh = (x.at(e) - ch.mu) * ch.r;
+            Jet<K, float> ge;
+            if (!a.relu || y0.v[e] > 0.f) ge = g.at(e);
+            const Jet<K, float> u = ch.gam * ge - m1 - xh * m2;
+            const Jet<K, float> xb = ch.r * u;
+            out.v[e] += xb.c[K];
+        }
+        st_pack<VEC>(a.xbar, ii, out);
+    });
 }
 
 
-template <int K> __global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) { bn_fwd_stats_body<K>(a); }
-template <int K> __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) { bn_fwd_apply_body<K>(a); }
-template <int K> __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) { bn_bwd_stats_body<K>(a); }
-template <int K> __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float ps) { bn_bwd_apply_body<K>(a, ps); }
+template <int K, int VEC> __global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) { bn_fwd_stats_body<K, VEC>(a); }
+template <int K, int VEC> __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) { bn_fwd_apply_body<K, VEC>(a); }
+template <int K, int VEC> __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) { bn_bwd_stats_body<K, VEC>(a); }
+template <int K, int VEC> __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float ps) { bn_bwd_apply_body<K, VEC>(a, ps); }
 
 // statistics + apply in ONE cooperative launch (grid-wide barrier between the two phases): halves the
 // number of dependent launches on the critical path of a pass; used when no cross-GPU reduction has to
 // happen between the phases.
-template <int K>
+template <int K, int VEC>
 __global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnArgs a, int do_stats) {
-    if (do_stats) bn_fwd_stats_body<K>(a);
+    if (do_stats) bn_fwd_stats_body<K, VEC>(a);
     __threadfence();
     cg::this_grid().sync();
-    bn_fwd_apply_body<K>(a);
+    bn_fwd_apply_body<K, VEC>(a);
 }
-template <int K>
+template <int K, int VEC>
 __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float ps) {
-    bn_bwd_stats_body<K>(a);
+    bn_bwd_stats_body<K, VEC>(a);
     __threadfence();
     cg::this_grid().sync();
-    bn_bwd_apply_body<K>(a, ps);
+    bn_bwd_apply_body<K, VEC>(a, ps);
 }
 
 template <typename F>
-static dim3 coop_grid(const BnArgs& a, F kernel) {
+static dim3 coop_grid(const BnArgs& a, int vec, F kernel, bool* fits) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
     if (per_sm < 1) per_sm = 1;
-    dim3 g = bn_grid(a);
+    dim3 g = bn_grid(a, vec);
     const long long cap = (long long)per_sm * kNumSMs;
     long long splits = g.y;
     if ((long long)g.x * splits > cap) splits = cap / g.x;
+    *fits = splits >= 1;                 // every block of a cooperative grid must be co-resident
     if (splits < 1) splits = 1;
     return dim3(g.x, (unsigned)splits);
 }
 
-template <int K>
+// (order, vector width) -> kernel instantiation
+#define B2S_BN_DISPATCH(order, vec, CALL)                                 \
+    do {                                                                  \
+        if ((vec) == 4) {                                                 \
+            if ((order) == 0) { CALL(0, 4); }                             \
+            else if ((order) == 1) { CALL(1, 4); }                        \
+            else { CALL(2, 4); }                                          \
+        } else {                                                          \
+            if ((order) == 0) { CALL(0, 1); }                             \
+            else if ((order) == 1) { CALL(1, 1); }                        \
+            else { CALL(2, 1); }                                          \
+        }                                                                 \
+    } while (0)
+
+template <int K, int VEC>
 static int launch_fwd_fused_t(cudaStream_t st, const BnArgs& a, int do_stats) {
-    const dim3 grid = coop_grid(a, bn_fwd_fused_kernel<K>);
-    if ((long long)grid.x * grid.y > (long long)kNumSMs * 4) {
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_fwd_fused_kernel<K>, 256, 0);
-        if ((long long)grid.x * grid.y > (long long)per_sm * kNumSMs) return 1;   // cannot be co-resident
-    }
+    bool fits = true;
+    const dim3 grid = coop_grid(a, VEC, bn_fwd_fused_kernel<K, VEC>, &fits);
+    if (!fits) return 1;
     BnArgs args = a;
     void* params[] = {(void*)&args, (void*)&do_stats};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_kernel<K>, grid, dim3(256), params, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_kernel<K, VEC>, grid, dim3(256), params, 0, st);
     if (e != cudaSuccess) { set_error("cooperative BN launch: %s", cudaGetErrorString(e)); return -3; }
     count_launch();
     return 0;
 }
-template <int K>
+template <int K, int VEC>
 static int launch_bwd_fused_t(cudaStream_t st, const BnArgs& a) {
-    const dim3 grid = coop_grid(a, bn_bwd_fused_kernel<K>);
-    if ((long long)grid.x * grid.y > (long long)kNumSMs * 4) {
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<K>, 256, 0);
-        if ((long long)grid.x * grid.y > (long long)per_sm * kNumSMs) return 1;
-    }
+    bool fits = true;
+    const dim3 grid = coop_grid(a, VEC, bn_bwd_fused_kernel<K, VEC>, &fits);
+    if (!fits) return 1;
     BnArgs args = a;
     float ps = a.pgrad_scale;
     void* params[] = {(void*)&args, (void*)&ps};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<K>, grid, dim3(256), params, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<K, VEC>, grid, dim3(256), params, 0, st);
     if (e != cudaSuccess) { set_error("cooperative BN launch: %s", cudaGetErrorString(e)); return -3; }
     count_launch();
     return 0;
@@ -311,56 +386,64 @@ static int launch_bwd_fused_t(cudaStream_t st, const BnArgs& a) {
 int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stats) {
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_fwd_fused", 16.0 * elems, 4.0 * elems * (2 * order + 3), st);
-    if (order == 0) return launch_fwd_fused_t<0>(st, a, do_stats);
-    if (order == 1) return launch_fwd_fused_t<1>(st, a, do_stats);
-    return launch_fwd_fused_t<2>(st, a, do_stats);
+    const int vec = bn_vec(a);
+#define CALL(K_, V_) return launch_fwd_fused_t<K_, V_>(st, a, do_stats)
+    B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
+    return -5;
 }
 int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_bwd_fused", 16.0 * elems, 4.0 * elems * (4 * order + 7), st);
-    if (order == 0) return launch_bwd_fused_t<0>(st, a);
-    if (order == 1) return launch_bwd_fused_t<1>(st, a);
-    return launch_bwd_fused_t<2>(st, a);
+    const int vec = bn_vec(a);
+#define CALL(K_, V_) return launch_bwd_fused_t<K_, V_>(st, a)
+    B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
+    return -5;
 }
 
 int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a) {
-    const dim3 grid = bn_grid(a);
+    const int vec = bn_vec(a);
+    const dim3 grid = bn_grid(a, vec);
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_fwd_stats", 8.0 * elems, 4.0 * elems * (order + 1), st);
-    if (order == 0) bn_fwd_stats_kernel<0><<<grid, 256, 0, st>>>(a);
-    else if (order == 1) bn_fwd_stats_kernel<1><<<grid, 256, 0, st>>>(a);
-    else bn_fwd_stats_kernel<2><<<grid, 256, 0, st>>>(a);
+#define CALL(K_, V_) bn_fwd_stats_kernel<K_, V_><<<grid, 256, 0, st>>>(a)
+    B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
     B2S_LAUNCH_CHECK();
     return 0;
 }
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a) {
-    const dim3 grid = bn_grid(a);
+    const int vec = bn_vec(a);
+    const dim3 grid = bn_grid(a, vec);
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_fwd_apply", 8.0 * elems, 4.0 * elems * (order + 2), st);
-    if (order == 0) bn_fwd_apply_kernel<0><<<grid, 256, 0, st>>>(a);
-    else if (order == 1) bn_fwd_apply_kernel<1><<<grid, 256, 0, st>>>(a);
-    else bn_fwd_apply_kernel<2><<<grid, 256, 0, st>>>(a);
+#define CALL(K_, V_) bn_fwd_apply_kernel<K_, V_><<<grid, 256, 0, st>>>(a)
+    B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
     B2S_LAUNCH_CHECK();
     return 0;
 }
 int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a) {
-    const dim3 grid = bn_grid(a);
+    const int vec = bn_vec(a);
+    const dim3 grid = bn_grid(a, vec);
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_bwd_stats", 8.0 * elems, 4.0 * elems * (2 * order + 3), st);
-    if (order == 0) bn_bwd_stats_kernel<0><<<grid, 256, 0, st>>>(a);
-    else if (order == 1) bn_bwd_stats_kernel<1><<<grid, 256, 0, st>>>(a);
-    else bn_bwd_stats_kernel<2><<<grid, 256, 0, st>>>(a);
+#define CALL(K_, V_) bn_bwd_stats_kernel<K_, V_><<<grid, 256, 0, st>>>(a)
+    B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
     B2S_LAUNCH_CHECK();
     return 0;
 }
 int launch_bn_bwd_apply(cudaStream_t st, int order, const BnArgs& a) {
-    const dim3 grid = bn_grid(a);
+    const int vec = bn_vec(a);
+    const dim3 grid = bn_grid(a, vec);
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_bwd_apply", 8.0 * elems, 4.0 * elems * (2 * order + 4), st);
     const float ps = a.pgrad_scale;
-    if (order == 0) bn_bwd_apply_kernel<0><<<grid, 256, 0, st>>>(a, ps);
-    else if (order == 1) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(a, ps);
-    else bn_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(a, ps);
+#define CALL(K_, V_) bn_bwd_apply_kernel<K_, V_><<<grid, 256, 0, st>>>(a, ps)
+    B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
     B2S_LAUNCH_CHECK();
     return 0;
 }
@@ -464,13 +547,13 @@ int bn_corr_sums() { return kCorrSums; }
 
 int launch_bn_corr_stats(cudaStream_t st, const BnArgs& a, const float* gc) {
     ProfScope prof("bn_corr_stats", 20.0 * a.batch * a.C * a.HW, 4.0 * 6 * (double)a.batch * a.C * a.HW, st);
-    bn_corr_stats_kernel<<<bn_grid(a), 256, 0, st>>>(a, gc);
+    bn_corr_stats_kernel<<<bn_grid(a, 1), 256, 0, st>>>(a, gc);
     B2S_LAUNCH_CHECK();
     return 0;
 }
 int launch_bn_corr_apply(cudaStream_t st, const BnArgs& a, const float* gc, float* xbar) {
     ProfScope prof("bn_corr_apply", 8.0 * a.batch * a.C * a.HW, 4.0 * 4 * (double)a.batch * a.C * a.HW, st);
-    bn_corr_apply_kernel<<<bn_grid(a), 256, 0, st>>>(a, gc, xbar, a.pgrad_scale);
+    bn_corr_apply_kernel<<<bn_grid(a, 1), 256, 0, st>>>(a, gc, xbar, a.pgrad_scale);
     B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -562,21 +562,22 @@ static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
 
 int launch_conv_fwd(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* act,
                     const float* const* wt, const float* scale, const float* bias, int relu_mode,
-                    const float* relu_ref, float* out, int accumulate) {
+                    const float* relu_ref, float* out, int accumulate, const float* const* pack) {
     ConvKArgs a{};
     a.g = g;
     a.npairs = npairs;
-    for (int p = 0; p < npairs; ++p) { a.act[p] = act[p]; a.wt[p] = wt[p]; a.scale[p] = scale[p]; }
+    for (int p = 0; p < npairs; ++p) { a.act[p] = act[p]; a.wt[p] = wt[p]; a.scale[p] = scale[p]; a.pack[p] = pack ? pack[p] : nullptr; }
     a.bias = bias; a.relu_mode = relu_mode; a.relu_ref = relu_ref; a.out = out; a.accumulate = accumulate;
     return launch_gather<MODE_FWD>(st, a);
 }
 
 int launch_conv_dgrad(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* adj,
-                      const float* const* wt, const float* scale, float* out, int accumulate) {
+                      const float* const* wt, const float* scale, float* out, int accumulate,
+                      const float* const* pack) {
     ConvKArgs a{};
     a.g = g;
     a.npairs = npairs;
-    for (int p = 0; p < npairs; ++p) { a.act[p] = adj[p]; a.wt[p] = wt[p]; a.scale[p] = scale[p]; }
+    for (int p = 0; p < npairs; ++p) { a.act[p] = adj[p]; a.wt[p] = wt[p]; a.scale[p] = scale[p]; a.pack[p] = pack ? pack[p] : nullptr; }
     a.bias = nullptr; a.relu_mode = 0; a.relu_ref = nullptr; a.out = out; a.accumulate = accumulate;
     return launch_gather<MODE_DGRAD>(st, a);
 }

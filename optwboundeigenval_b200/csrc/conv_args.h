@@ -8,6 +8,7 @@ struct ConvKArgs {
     ConvGeom g;
     const float* act[kMaxPairs];   // gather source (forward: x-like; dgrad: ybar-like; wgrad: x-like)
     const float* wt[kMaxPairs];    // weights (forward/dgrad) or adjoint (wgrad)
+    const float* pack[kMaxPairs];  // forward/dgrad: packed 3xTF32 image of wt[p] for the tcgen05 path, or NULL
     float scale[kMaxPairs];
     int npairs;
     const float* bias;
@@ -20,8 +21,24 @@ struct ConvKArgs {
 
 enum { MODE_FWD = 0, MODE_DGRAD = 1 };
 
-// tcgen05 / TMEM path for wide layers (conv_tc.cu). mode: MODE_FWD or MODE_DGRAD.
-// Returns 1 when the kernel was launched, 0 when the shape is not eligible, <0 on error.
+// ---- tcgen05 / TMEM path (conv_tc.cu) -------------------------------------------------------------
+// One weight tensor of one layer in one contraction mode, to be split (hi/lo TF32) and laid out as the
+// shared-memory images of its k-blocks.  `begin` = running element count over the job list.
+struct TcPackJob {
+    long long src_off;   // offset of the weight tensor in the flat parameter vector
+    long long dst_off;   // float offset of its image in the pack buffer
+    long long begin;
+    int Cs, Cd;          // source / destination channels of the contraction
+    int KHW, mode, BN, nchunks;
+};
+int tc_choose_bn(int Cd);
+long long tc_pack_floats(int Cs, int Cd, int KHW);      // size of one packed image
+bool tc_shape_ok(int Cs, int Cd, int Hs, int Ws);
+// packs every job: dst_base[job.dst_off ...] <- split(src_base[job.src_off ...]); total = sum of job elements
+int launch_tc_pack(cudaStream_t st, const TcPackJob* d_jobs, int njobs, long long total, const float* src_base,
+                   float* dst_base);
+// mode: MODE_FWD or MODE_DGRAD.  Returns 1 when the kernel was launched, 0 when the layer is not
+// eligible (no packed image, too few pixels), <0 on error.
 int try_launch_conv_tc(int mode, cudaStream_t st, const ConvKArgs& a);
 // 0 = never, 1 = automatic (default), 2 = whenever legal (tests)
 void set_tc_mode(int mode);

@@ -22,10 +22,11 @@ struct ConvGeom {
 //   relu_mode 0: none, 1: out = max(out, 0), 2: out = relu_ref > 0 ? out : 0
 int launch_conv_fwd(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* act,
                     const float* const* wt, const float* scale, const float* bias, int relu_mode,
-                    const float* relu_ref, float* out, int accumulate);
+                    const float* relu_ref, float* out, int accumulate, const float* const* pack = nullptr);
 // xbar (+)= sum_p scale[p] * conv^T(adj[p], wt[p])
 int launch_conv_dgrad(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* adj,
-                      const float* const* wt, const float* scale, float* out, int accumulate);
+                      const float* const* wt, const float* scale, float* out, int accumulate,
+                      const float* const* pack = nullptr);
 // wbar += sum_p scale[p] * corr(act[p], adj[p])   (atomic accumulation into the flat vector)
 int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const float* const* act,
                       const float* const* adj, const float* scale, float* wbar);

@@ -157,6 +157,14 @@ struct b2s_plan {
     long long kfac_m_elems = 0;
     double* kfac_tr = nullptr;        // T r
 
+    // tcgen05 path: packed 3xTF32 weight images (conv_tc.cu)
+    std::vector<long long> tc_off[2];   // per op index and mode: float offset of the image, -1 = not packed
+    TcPackJob* tc_jobs = nullptr;       // device copy of the job list
+    int tc_njobs = 0;
+    long long tc_total = 0;             // elements over all jobs
+    float* tc_packW = nullptr;          // images of the parameters (rebuilt by every base pass)
+    float* tc_packV = nullptr;          // images of the tangent direction (rebuilt by every order-1 pass)
+
     b2s_pistate* pi = nullptr;
     Comm* comm = nullptr;
     int world = 1;
@@ -235,9 +243,20 @@ static BnArgs bn_args(b2s_plan* p, int oi, int K) {
     return a;
 }
 
+// packed image of a weight operand (W lives in p->params, V in p->v32), NULL when the layer is not packed
+static inline const float* tc_image(const b2s_plan* p, int oi, int mode, const float* wt) {
+    if (!p->tc_packW || p->tc_off[mode][oi] < 0) return nullptr;
+    const bool is_v = wt >= p->v32 && wt < p->v32 + p->P;
+    return (is_v ? p->tc_packV : p->tc_packW) + p->tc_off[mode][oi];
+}
+
 // ---- forward sweep of order K -----------------------------------------------------------------
 static int forward(b2s_plan* p, int K) {
     cudaStream_t st = p->stream;
+    if (p->tc_njobs > 0 && get_tc_mode() != 0) {
+        if (K == 0) B2S_TRY(launch_tc_pack(st, p->tc_jobs, p->tc_njobs, p->tc_total, p->params, p->tc_packW));
+        if (K == 1) B2S_TRY(launch_tc_pack(st, p->tc_jobs, p->tc_njobs, p->tc_total, p->v32, p->tc_packV));
+    }
     if (p->bn_total > 0) B2S_CUDA(cudaMemsetAsync(p->fsum[K], 0, (size_t)p->bn_total * sizeof(double), st));
     for (size_t oi = 0; oi < p->ops.size(); ++oi) {
         const b2s_op& op = p->ops[oi];
@@ -270,7 +289,9 @@ static int forward(b2s_plan* p, int K) {
                 act[np] = tptr(p, p->fw, 2, op.in); wt[np] = W; sc[np] = 1.f; ++np;
                 act[np] = tptr(p, p->fw, 1, op.in); wt[np] = V; sc[np] = 2.f; ++np;
             }
-            B2S_TRY(launch_conv_fwd(st, g, np, act, wt, sc, bias, relu ? (K == 0 ? 1 : 2) : 0, y0, out, 0));
+            const float* pk[kMaxPairs];
+            for (int q = 0; q < np; ++q) pk[q] = tc_image(p, (int)oi, MODE_FWD, wt[q]);
+            B2S_TRY(launch_conv_fwd(st, g, np, act, wt, sc, bias, relu ? (K == 0 ? 1 : 2) : 0, y0, out, 0, pk));
             break;
         }
         case B2S_OP_BN: {
@@ -380,7 +401,9 @@ static int backward(b2s_plan* p, int K) {
                 np = 0;
                 a_[np] = gk[K]; b_[np] = W; sc[np] = 1.f; ++np;
                 if (K >= 1) { a_[np] = gk[K - 1]; b_[np] = V; sc[np] = K == 2 ? 2.f : 1.f; ++np; }
-                B2S_TRY(launch_conv_dgrad(st, g, np, a_, b_, sc, tptr(p, p->bw, K, op.in), acc));
+                const float* pk[kMaxPairs];
+                for (int q = 0; q < np; ++q) pk[q] = tc_image(p, oi, MODE_DGRAD, b_[q]);
+                B2S_TRY(launch_conv_dgrad(st, g, np, a_, b_, sc, tptr(p, p->bw, K, op.in), acc, pk));
             }
             break;
         }
@@ -453,7 +476,10 @@ static int backward_correction(b2s_plan* p) {
             B2S_TRY(launch_conv_wgrad(p->side, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
             if (op.b_off >= 0)
                 B2S_TRY(launch_bias_grad(p->side, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
-            if (!first) B2S_TRY(launch_conv_dgrad(st, g, 1, &gc, &W, &one, tptr(p, p->bw, 2, op.in), acc));
+            if (!first) {
+                const float* pk = tc_image(p, oi, MODE_DGRAD, W);
+                B2S_TRY(launch_conv_dgrad(st, g, 1, &gc, &W, &one, tptr(p, p->bw, 2, op.in), acc, &pk));
+            }
             break;
         }
         case B2S_OP_BN: {
@@ -718,6 +744,46 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     cudaMemsetAsync(p->v32, 0, (size_t)(n_params + 4) * sizeof(float), p->stream);
     cudaMemsetAsync(p->params, 0, (size_t)(n_params + 4) * sizeof(float), p->stream);
     p->workspace += 2 * (n_params + 4) * 4 + (long long)lab * 8;
+    {   // tcgen05 path: one pack job per eligible (Conv/Linear op, contraction mode); ops that share a
+        // weight tensor (forest's fc2) get their own image -- the geometry could differ
+        std::vector<TcPackJob> jobs;
+        long long floats = 0, elems = 0;
+        p->tc_off[0].assign(n_ops, -1);
+        p->tc_off[1].assign(n_ops, -1);
+        for (int i = 0; i < n_ops; ++i) {
+            const b2s_op& op = ops[i];
+            if (op.kind != B2S_OP_CONV) continue;
+            const b2s_tensor& I = tensors[op.in];
+            const b2s_tensor& O = tensors[op.out];
+            for (int mode = 0; mode < 2; ++mode) {
+                if (mode == MODE_DGRAD && (op.flags & B2S_F_FIRST)) continue;
+                const int Cs = mode == MODE_FWD ? I.C : O.C, Cd = mode == MODE_FWD ? O.C : I.C;
+                const int Hs = mode == MODE_FWD ? I.H : O.H, Ws = mode == MODE_FWD ? I.W : O.W;
+                if (!tc_shape_ok(Cs, Cd, Hs, Ws)) continue;
+                TcPackJob jb{};
+                jb.src_off = op.w_off; jb.dst_off = floats; jb.begin = elems;
+                jb.Cs = Cs; jb.Cd = Cd; jb.KHW = op.kh * op.kw; jb.mode = mode;
+                jb.BN = tc_choose_bn(Cd); jb.nchunks = (Cs + 31) / 32;
+                const long long f = tc_pack_floats(Cs, Cd, jb.KHW);
+                p->tc_off[mode][i] = floats;
+                floats += f;
+                elems += f / 2;
+                jobs.push_back(jb);
+            }
+        }
+        if (!jobs.empty()) {
+            if (cudaMalloc(&p->tc_jobs, jobs.size() * sizeof(TcPackJob)) != cudaSuccess ||
+                cudaMalloc(&p->tc_packW, (size_t)floats * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&p->tc_packV, (size_t)floats * sizeof(float)) != cudaSuccess) {
+                set_error("b2s_plan_create: out of device memory (packed weight images)");
+                return fail(-2);
+            }
+            cudaMemcpy(p->tc_jobs, jobs.data(), jobs.size() * sizeof(TcPackJob), cudaMemcpyHostToDevice);
+            p->tc_njobs = (int)jobs.size();
+            p->tc_total = elems;
+            p->workspace += 2 * floats * 4;
+        }
+    }
     for (int i = 0; i < n_ops; ++i) {
         if (ops[i].kind == B2S_OP_MAXPOOL) {
             const b2s_tensor& O = tensors[ops[i].out];
@@ -745,6 +811,7 @@ int b2s_plan_destroy(b2s_plan* p) {
     }
     for (auto a : p->argmax) cudaFree(a);
     cudaFree(p->csum); cudaFree(p->out_corr);
+    cudaFree(p->tc_jobs); cudaFree(p->tc_packW); cudaFree(p->tc_packV);
     cudaFree(p->kfac_m); cudaFree(p->kfac_tr);
     cudaFree(p->params); cudaFree(p->v32); cudaFree(p->loss);
     cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
