@@ -17,6 +17,7 @@ struct ConvKArgs {
     float* out;
     int accumulate;
     int k_chunk;                   // wgrad: K elements per blockIdx.z
+    long long* trace;              // debug (B2S_TC_TRACE=1): per-role clock64 stamps of CTA 0, else NULL
 };
 
 enum { MODE_FWD = 0, MODE_DGRAD = 1 };

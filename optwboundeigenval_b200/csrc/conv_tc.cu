@@ -16,20 +16,22 @@
 //      other TMEM buffer.
 //
 // Data movement, per CTA (persistent over output tiles), warp-specialised:
-//   warps 0-3  A transform: lane = pixel (coalesced NCHW reads, im2col on the fly with zero padding),
-//              split hi/lo in registers, tcgen05.st straight into TMEM -- the A operand never touches
-//              shared memory (tcgen05.mma with A in TMEM), no bank conflicts, no proxy fence;
-//   warp  9    B producer: weights are pre-split and pre-arranged ONCE per pass by tc_pack_kernel into
+//   warps 0-7  A transform (two warpgroups on alternate k-blocks, loads of the next k-block in flight
+//              while the current one is converted): lane = pixel (coalesced NCHW reads, im2col on the fly
+//              with zero padding), split hi/lo in registers, tcgen05.st straight into TMEM -- the A operand
+//              never touches shared memory (tcgen05.mma with A in TMEM), no bank conflicts, no proxy fence;
+//   warp  13   B producer: weights are pre-split and pre-arranged ONCE per pass by tc_pack_kernel into
 //              the exact shared-memory image (K-major, SWIZZLE_NONE core matrices) of every k-block,
 //              so a stage is one cp.async.bulk (bulk-copy engine, mbarrier complete_tx);
-//   warp  8    MMA issuer: one thread, 3 x tcgen05.mma.kind::tf32 per k-step, tcgen05.commit to the
+//   warp  12   MMA issuer: one thread, 3 x tcgen05.mma.kind::tf32 per k-step, tcgen05.commit to the
 //              stage-free and accumulator-full mbarriers;
-//   warps 4-7  drain + epilogue: tcgen05.ld the block accumulator, acc += scale * d, and after the last
+//   warps 8-11 drain + epilogue (setmaxnreg gives this warpgroup 208 registers): tcgen05.ld the block accumulator, acc += scale * d, and after the last
 //              k-block bias / ReLU mask / accumulate and coalesced NCHW stores (lane = pixel).
 // Four stages of A (TMEM) and B (smem); two accumulator buffers.  Descriptor encodings follow
 // cute/arch/mma_sm100_desc.hpp and cute/arch/mma_sm100_umma.hpp (SM100_MMA_TF32_TS).
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "conv_args.h"
 
@@ -46,10 +48,23 @@ int get_tc_mode() { return g_tc_mode; }
 
 constexpr int TC_M = 128;        // pixels per tile (UMMA M, cta_group::1)
 constexpr int TC_KB = 32;        // k per k-block = 4 UMMA k-steps of 8 (tf32)
-constexpr int TC_NST = 4;        // pipeline stages (A in TMEM, B in shared memory)
+constexpr int TC_NST = 3;        // pipeline stages (A in TMEM, B in shared memory)
 constexpr int TC_ACOLS = 64;     // TMEM columns per A stage: 32 hi + 32 lo
-constexpr int TC_DCOL0 = TC_NST * TC_ACOLS;    // first accumulator column (two buffers of BN columns)
-constexpr int TC_THREADS = 320;  // 10 warps, roles above
+constexpr int TC_DCOL0 = TC_NST * TC_ACOLS;    // first accumulator column
+constexpr int TC_DCOLS = (512 - TC_DCOL0) / 2; // columns of one of the two accumulator buffers (160)
+// Consecutive tcgen05.mma into the SAME accumulator serialise on its ~90-clock read-modify-write latency
+// (measured: 12 dependent MMAs take ~1100 clocks whether N is 16 or 128).  Narrow tiles therefore spread
+// the three 3xTF32 terms (hi*lo, lo*hi, hi*hi) -- and for BN = 16 also odd / even k-steps -- over
+// independent accumulators inside the buffer; the drain adds them up.
+__host__ __device__ constexpr int tc_nacc(int BN) { return 6 * BN <= TC_DCOLS ? 6 : 3 * BN <= TC_DCOLS ? 3 : 2 * BN <= TC_DCOLS ? 2 : 1; }
+constexpr int TC_THREADS = 512;  // four warpgroups: 2 x A transform, drain, {MMA issuer, B producer, 2 idle warps}
+constexpr int TC_WARP_MMA = 12;
+constexpr int TC_WARP_B = 13;
+// registers per thread after the role split (setmaxnreg): 128 (launch) for the transform warpgroups,
+// TC_REGS_DRAIN for the warpgroup that holds up to 128 accumulators per thread, TC_REGS_MISC for the rest;
+// 128 * (128 + 128 + 208 + 40) <= 64 K registers
+constexpr int TC_REGS_DRAIN = 208;
+constexpr int TC_REGS_MISC = 40;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,22 +110,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait: a protocol error must become a trap (launch failure), never a hang
+__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done;
+}
+// bounded wait: a protocol error must become a trap (launch failure), never a hang.  The clock is only
+// read once the first probe has failed (the issuing thread's fast path is a single try_wait).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    if (mbar_try(addr, parity)) return;
     const long long t0 = clock64();
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
+    while (!mbar_try(addr, parity)) {
         if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
     }
 }
@@ -124,6 +143,20 @@ __device__ __forceinline__ uint32_t to_tf32_bits(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
+}
+// one lane of a converged warp; operands computed warp-uniformly OUTSIDE the elected branch stay in uniform
+// registers, so each tcgen05.mma is a single UTCHMMA (a branch on lane == 0 makes the compiler wrap every
+// MMA in an R2UR broadcast loop: ~90 clocks per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -215,14 +248,166 @@ int launch_tc_pack(cudaStream_t st, const TcPackJob* d_jobs, int njobs, long lon
 // ---------------------------------------------------------------------------------------------
 // the contraction
 // ---------------------------------------------------------------------------------------------
+// Walks the k-blocks of this CTA in issue order: tile (persistent stride), pair, tap, channel chunk.
+// The A-transform warps keep the per-pixel gather state here (one thread = one pixel row of the tile).
+// lanes whose tap falls outside the image read this instead (stride 0): their loads need no predicate
+__device__ const float tc_zero_words[4] = {0.f, 0.f, 0.f, 0.f};
+
+template <int MODE>
+struct TcCursor {
+    // geometry is re-read from the kernel parameters (constant bank) instead of being cached in
+    // registers: this role keeps two 32-value load buffers live
+    const ConvKArgs& a;
+    int r;                 // pixel row of this thread inside the tile
+    int tile, p, ky, kx, cc;
+    uint32_t kbg;
+    int y, x;              // destination pixel (y < 0: past the end of the pixel range)
+    long long nbase;       // sample offset in the source
+    const float* src;      // channel 0 of the current (pair, tap) at this thread's pixel, or the zero word
+    long long cstride;     // elements between consecutive source channels for this thread (0 on the zero word)
+
+    __device__ __forceinline__ int Hd() const { return MODE == MODE_FWD ? a.g.OH : a.g.H; }
+    __device__ __forceinline__ int Wd() const { return MODE == MODE_FWD ? a.g.OW : a.g.W; }
+    __device__ __forceinline__ int Cs() const { return MODE == MODE_FWD ? a.g.Cin : a.g.Cout; }
+    __device__ __forceinline__ int Hs() const { return MODE == MODE_FWD ? a.g.H : a.g.OH; }
+    __device__ __forceinline__ int Ws() const { return MODE == MODE_FWD ? a.g.W : a.g.OW; }
+    __device__ __forceinline__ long long s_ss() const { return MODE == MODE_FWD ? a.g.in_sstride : a.g.out_sstride; }
+    __device__ __forceinline__ long long J() const { return (long long)a.g.batch * (Hd() * Wd()); }
+    __device__ __forceinline__ int n_jt() const { return (int)((J() + TC_M - 1) / TC_M); }
+    __device__ __forceinline__ int nchunks() const { return (Cs() + TC_KB - 1) / TC_KB; }
+
+    __device__ __forceinline__ TcCursor(const ConvKArgs& a_, int r_) : a(a_), r(r_) {}
+    __device__ __forceinline__ void start(int total_tiles) {
+        tile = blockIdx.x; p = 0; ky = 0; kx = 0; cc = 0; kbg = 0;
+        if (tile < total_tiles) { set_tile(); set_tap(); }
+    }
+    __device__ __forceinline__ void set_tile() {
+        const int jt = tile % n_jt();
+        const long long j = (long long)jt * TC_M + r;
+        const int HWd = Hd() * Wd();
+        y = -1; x = 0; nbase = 0;
+        if (j < J()) {
+            const int n = (int)(j / HWd);
+            const int pix = (int)(j - (long long)n * HWd);
+            y = pix / Wd();
+            x = pix - y * Wd();
+            nbase = (long long)n * s_ss();
+        }
+    }
+    __device__ __forceinline__ void set_tap() {
+        const ConvGeom& g = a.g;
+        int sy, sx;
+        bool ok;
+        if (MODE == MODE_FWD) {
+            sy = y * g.sh + ky - g.ph; sx = x * g.sw + kx - g.pw;
+            ok = sy >= 0 && sy < Hs() && sx >= 0 && sx < Ws();
+        } else {
+            const int ty_ = y + g.ph - ky, tx_ = x + g.pw - kx;
+            sy = ty_ / g.sh; sx = tx_ / g.sw;
+            ok = ty_ >= 0 && tx_ >= 0 && sy * g.sh == ty_ && sx * g.sw == tx_ && sy < Hs() && sx < Ws();
+        }
+        ok = ok && y >= 0;
+        src = ok ? a.act[p] + nbase + (sy * Ws() + sx) : tc_zero_words;
+        cstride = ok ? (long long)Hs() * Ws() : 0;
+    }
+    __device__ __forceinline__ int nvalid() const { return min(TC_KB, Cs() - cc * TC_KB); }
+    // returns false when the CTA has no further k-block
+    __device__ __forceinline__ bool advance(int total_tiles) {
+        ++kbg;
+        if (++cc < nchunks()) return true;
+        cc = 0;
+        if (++kx == a.g.KW) {
+            kx = 0;
+            if (++ky == a.g.KH) {
+                ky = 0;
+                if (++p == a.npairs) {
+                    p = 0;
+                    tile += gridDim.x;
+                    if (tile >= total_tiles) return false;
+                    set_tile();
+                }
+            }
+        }
+        set_tap();
+        return true;
+    }
+    // the 32 (zero padded) source channels of the current k-block: all loads independent, unpredicated
+    // (out-of-image lanes read the zero word), addresses by pointer increments; only a ragged last group
+    // of 8 channels pays per-channel selects
+    __device__ __forceinline__ void load(float (&v)[TC_KB]) const {
+        const int nv = nvalid();
+        const float* __restrict__ ptr = src + (long long)cc * TC_KB * cstride;
+#pragma unroll
+        for (int g8 = 0; g8 < TC_KB / 8; ++g8) {
+            if (g8 * 8 + 8 <= nv) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[g8 * 8 + i] = __ldg(ptr); ptr += cstride; }
+            } else if (g8 * 8 < nv) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool in = g8 * 8 + i < nv;
+                    v[g8 * 8 + i] = in ? __ldg(ptr) : 0.f;
+                    if (in) ptr += cstride;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g8 * 8 + i] = 0.f;
+            }
+        }
+    }
+};
+
+// debug timeline: trace[(role * TC_TRACE_KB + kbg) * 4 + slot] = clock64(), CTA 0, first TC_TRACE_KB k-blocks
+constexpr int TC_TRACE_KB = 48;
+__device__ __forceinline__ void tc_stamp(long long* trace, int role, uint32_t kbg, int slot) {
+    if (trace && blockIdx.x == 0 && kbg < TC_TRACE_KB) trace[((size_t)role * TC_TRACE_KB + kbg) * 4 + slot] = clock64();
+}
+
+// split one k-block of A values and hand it to the tensor core: wait for the TMEM stage, tcgen05.st
+// hi / lo, publish on a_full
+__device__ __forceinline__ void tc_commit_a(const float (&v)[TC_KB], uint32_t kbg, int ksteps, uint32_t lane_addr,
+                                            uint64_t* a_full, uint64_t* ab_free, long long* trace) {
+    const int s = kbg % TC_NST;
+    const uint32_t round = kbg / TC_NST;
+    const bool tr = (threadIdx.x & 127) == 0;
+    if (tr) tc_stamp(trace, 0, kbg, 0);
+    if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
+    __syncwarp();
+    tc_fence_after();
+    if (tr) tc_stamp(trace, 0, kbg, 1);
+    const uint32_t col = (uint32_t)(s * TC_ACOLS);
+#pragma unroll
+    for (int ks = 0; ks < TC_KB / 8; ++ks) {
+        if (ks < ksteps) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // hi = round-to-nearest TF32; lo = f - hi is exact (<= 12 significant bits) and is cut to
+                // TF32 by clearing its low 13 bits (2^-22 relative to f; one conversion-pipe op per element)
+                const float f = v[ks * 8 + i];
+                hi[i] = to_tf32_bits(f);
+                lo[i] = __float_as_uint(f - __uint_as_float(hi[i])) & 0xffffe000u;
+            }
+            tmem_st8(lane_addr + col + ks * 8, hi);
+            tmem_st8(lane_addr + col + 32 + ks * 8, lo);
+        }
+    }
+    if (tr) tc_stamp(trace, 0, kbg, 2);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    mbar_arrive(&a_full[s]);
+    if (tr) tc_stamp(trace, 0, kbg, 3);
+}
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs a) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     constexpr int B_TILE_FLOATS = BN * TC_KB;                 // one of hi / lo
     constexpr uint32_t B_STAGE_BYTES = 2u * B_TILE_FLOATS * sizeof(float);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + TC_NST * B_STAGE_BYTES);
-    uint64_t* a_full = bars;                   // [NST] 128 transform threads arrive
-    uint64_t* b_full = bars + TC_NST;          // [NST] bulk copy complete_tx
+    uint64_t* a_full = bars;                   // [NST] operands landed: the 128 transform threads of the owning group
+                                               //       + the B producer's arrive.expect_tx and the bulk copy's bytes
+    uint64_t* b_full = a_full;                 // (same barrier)
     uint64_t* ab_free = bars + 2 * TC_NST;     // [NST] tcgen05.commit: the MMAs have read the stage
     uint64_t* d_full = bars + 3 * TC_NST;      // [2]   tcgen05.commit: block accumulator complete
     uint64_t* d_empty = d_full + 2;            // [2]   128 drain threads arrive
@@ -234,11 +419,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
     const int Wd = MODE == MODE_FWD ? g.OW : g.W;
     const long long d_ss = MODE == MODE_FWD ? g.out_sstride : g.in_sstride;
     const int Cs = MODE == MODE_FWD ? g.Cin : g.Cout;
-    const int Hs = MODE == MODE_FWD ? g.H : g.OH;
-    const int Ws = MODE == MODE_FWD ? g.W : g.OW;
-    const long long s_ss = MODE == MODE_FWD ? g.in_sstride : g.out_sstride;
     const int KHW = g.KH * g.KW;
-    const int HWd = Hd * Wd, HWs = Hs * Ws;
+    const int HWd = Hd * Wd;
     const long long J = (long long)g.batch * HWd;
     const int nchunks = (Cs + TC_KB - 1) / TC_KB;
     const int KBp = KHW * nchunks;                            // k-blocks per pair
@@ -250,8 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
 
     if (tid == 0) {
         for (int s = 0; s < TC_NST; ++s) {
-            mbar_init(&a_full[s], 128);
-            mbar_init(&b_full[s], 1);
+            mbar_init(&a_full[s], 128 + 1);
             mbar_init(&ab_free[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -260,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == TC_WARP_MMA) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                      : "memory");
@@ -271,77 +452,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ===================== A transform: global -> registers (split) -> TMEM =====================
-        const int r = warp * 32 + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t kbg = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int jt = tile % n_jt;
-            const long long j = (long long)jt * TC_M + r;
-            const bool in_range = j < J;
-            int n = 0, y = 0, x = 0;
-            if (in_range) {
-                n = (int)(j / HWd);
-                const int pix = (int)(j - (long long)n * HWd);
-                y = pix / Wd;
-                x = pix - y * Wd;
-            }
-            for (int p = 0; p < a.npairs; ++p) {
-                const float* __restrict__ plane0 = a.act[p] + (long long)n * s_ss;
-                for (int t = 0; t < KHW; ++t) {
-                    const int ky = t / g.KW, kx = t - ky * g.KW;
-                    int sy, sx;
-                    bool ok;
-                    if (MODE == MODE_FWD) {
-                        sy = y * g.sh + ky - g.ph; sx = x * g.sw + kx - g.pw;
-                        ok = sy >= 0 && sy < Hs && sx >= 0 && sx < Ws;
-                    } else {
-                        const int ty_ = y + g.ph - ky, tx_ = x + g.pw - kx;
-                        sy = ty_ / g.sh; sx = tx_ / g.sw;
-                        ok = ty_ >= 0 && tx_ >= 0 && sy * g.sh == ty_ && sx * g.sw == tx_ && sy < Hs && sx < Ws;
-                    }
-                    ok = ok && in_range;
-                    const float* __restrict__ src = plane0 + (ok ? sy * Ws + sx : 0);
-                    for (int cc = 0; cc < nchunks; ++cc) {
-                        const int nvalid = min(TC_KB, Cs - cc * TC_KB);
-                        const int ksteps = (nvalid + 7) >> 3;
-                        const int s = kbg % TC_NST;
-                        const uint32_t round = kbg / TC_NST;
-                        // issue the loads before waiting for the stage: they only need registers
-                        float v[TC_KB];
-                        const float* __restrict__ sc_ = src + (long long)cc * TC_KB * HWs;
-#pragma unroll
-                        for (int c = 0; c < TC_KB; ++c) v[c] = (ok && c < nvalid) ? __ldg(sc_ + (long long)c * HWs) : 0.f;
-                        if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
-                        __syncwarp();
-                        tc_fence_after();
-                        const uint32_t col = (uint32_t)(s * TC_ACOLS);
-#pragma unroll
-                        for (int ks = 0; ks < TC_KB / 8; ++ks) {
-                            if (ks < ksteps) {
-                                uint32_t hi[8], lo[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float f = v[ks * 8 + i];
-                                    hi[i] = to_tf32_bits(f);
-                                    lo[i] = to_tf32_bits(f - __uint_as_float(hi[i]));
-                                }
-                                tmem_st8(lane_addr + col + ks * 8, hi);
-                                tmem_st8(lane_addr + col + 32 + ks * 8, lo);
-                            }
-                        }
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        tc_fence_before();
-                        mbar_arrive(&a_full[s]);
-                        ++kbg;
-                    }
-                }
-            }
+        // two warpgroups take alternate k-blocks; each keeps the loads of its NEXT k-block in flight while
+        // it converts and stores the current one (two register buffers)
+        const int grp = warp >> 2, q = warp & 3;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        TcCursor<MODE> c(a, q * 32 + lane);
+        c.start(total_tiles);
+        bool more = c.tile < total_tiles;
+        if (grp == 1 && more) more = c.advance(total_tiles);
+        float va[TC_KB], vb[TC_KB];
+        uint32_t ka = 0, kb = 0;
+        int sa = 0, sb = 0;
+        // fetch(): issue the loads of this group's next k-block and step the cursor two k-blocks on
+#define TC_FETCH(V, KI, SI)                                           \
+        do {                                                          \
+            if ((tid & 127) == 0) tc_stamp(a.trace, 3, c.kbg, 0);      \
+            c.load(V); KI = c.kbg; SI = (c.nvalid() + 7) >> 3;         \
+            if ((tid & 127) == 0) tc_stamp(a.trace, 3, KI, 1);         \
+            more = c.advance(total_tiles);                            \
+            if (more) more = c.advance(total_tiles);                  \
+            if ((tid & 127) == 0) tc_stamp(a.trace, 3, KI, 2);         \
+        } while (0)
+        bool ha = more;
+        if (ha) TC_FETCH(va, ka, sa);
+        while (ha) {
+            const bool hb = more;
+            if (hb) TC_FETCH(vb, kb, sb);
+            tc_commit_a(va, ka, sa, lane_addr, a_full, ab_free, a.trace);
+            if (!hb) break;
+            ha = more;
+            if (ha) TC_FETCH(va, ka, sa);
+            tc_commit_a(vb, kb, sb, lane_addr, a_full, ab_free, a.trace);
         }
-    } else if (warp < 8) {
+#undef TC_FETCH
+    } else if (warp < 12) {
         // ===================== drain + epilogue: TMEM -> fp32 registers -> NCHW global ===============
-        const int q = warp - 4;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_DRAIN));
+        const int q = warp - 8;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t kbg = 0;
@@ -350,103 +499,158 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
             float acc[BN];
 #pragma unroll
             for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+            constexpr int NACC = tc_nacc(BN);
+            const int last_ksteps = (Cs - (nchunks - 1) * TC_KB + 7) >> 3;
             for (int p = 0; p < a.npairs; ++p) {
                 const float sc = a.scale[p];
                 for (int kbl = 0; kbl < KBp; ++kbl) {
                     const int b = kbg & 1;
+                    if (tid == 256) tc_stamp(a.trace, 2, kbg, 0);
                     mbar_wait(&d_full[b], (kbg >> 1) & 1);
                     __syncwarp();
                     tc_fence_after();
+                    if (tid == 256) tc_stamp(a.trace, 2, kbg, 1);
+                    // with 6 accumulators the odd-k-step set is only written by k-blocks of >= 2 k-steps
+                    const bool odd_set = NACC == 6 && (((kbl % nchunks) == nchunks - 1 ? last_ksteps : TC_KB / 8) >= 2);
+                    const uint32_t d0 = lane_addr + TC_DCOL0 + b * TC_DCOLS;
 #pragma unroll
                     for (int c0 = 0; c0 < BN; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(lane_addr + TC_DCOL0 + b * BN + c0, v);
+                        uint32_t v[NACC >= 3 ? 3 : NACC][16];
+#pragma unroll
+                        for (int q2 = 0; q2 < (NACC >= 3 ? 3 : NACC); ++q2) tmem_ld16(d0 + q2 * BN + c0, v[q2]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(__uint_as_float(v[i]), sc, acc[c0 + i]);
+                        for (int i = 0; i < 16; ++i) {
+                            float d = __uint_as_float(v[0][i]);
+                            if (NACC >= 2) d += __uint_as_float(v[1][i]);
+                            if (NACC >= 3) d += __uint_as_float(v[2][i]);
+                            acc[c0 + i] = fmaf(d, sc, acc[c0 + i]);
+                        }
+                        if (NACC == 6 && odd_set) {
+                            uint32_t w[3][16];
+#pragma unroll
+                            for (int q2 = 0; q2 < 3; ++q2) tmem_ld16(d0 + (3 + q2) * BN + c0, w[q2]);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                acc[c0 + i] = fmaf(__uint_as_float(w[0][i]) + __uint_as_float(w[1][i]) + __uint_as_float(w[2][i]), sc, acc[c0 + i]);
+                        }
                     }
                     tc_fence_before();
                     mbar_arrive(&d_empty[b]);
+                    if (tid == 256) tc_stamp(a.trace, 2, kbg, 2);
                     ++kbg;
                 }
             }
+            // epilogue: lane = pixel, so every per-channel store is one coalesced 128-byte row.  Reads the
+            // epilogue depends on (previous adjoint, ReLU reference) are issued in batches of 8 ahead of
+            // the stores so that they overlap instead of forming a load -> store chain.
             const long long j = (long long)jt * TC_M + r;
             if (j < J) {
                 const int n = (int)(j / HWd);
                 const int pix = (int)(j - (long long)n * HWd);
-                const long long base = (long long)n * d_ss + pix;
                 const int m0 = nt * BN;
+                float* __restrict__ outp = a.out + (long long)n * d_ss + pix + (long long)m0 * HWd;
+                const float* __restrict__ refp = a.relu_mode == 2 ? a.relu_ref + (long long)n * d_ss + pix + (long long)m0 * HWd : nullptr;
+                const float* __restrict__ bias = a.bias;
+                const int mrem = Cd - m0;                 // valid channels of this tile
+                const bool need_out = a.accumulate != 0;
 #pragma unroll
-                for (int i = 0; i < BN; ++i) {
-                    const int m = m0 + i;
-                    if (m < Cd) {
-                        const long long o = base + (long long)m * HWd;
-                        float val = acc[i];
-                        if (a.bias) val += a.bias[m];
-                        if (a.accumulate) val += a.out[o];
-                        if (a.relu_mode == 1) val = val > 0.f ? val : 0.f;
-                        else if (a.relu_mode == 2) val = a.relu_ref[o] > 0.f ? val : 0.f;
-                        a.out[o] = val;
+                for (int i0 = 0; i0 < BN; i0 += 8) {
+                    float prev[8], ref[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool okc = i0 + i < mrem;
+                        prev[i] = (need_out && okc) ? outp[(long long)(i0 + i) * HWd] : 0.f;
+                        ref[i] = (refp && okc) ? __ldg(refp + (long long)(i0 + i) * HWd) : 1.f;
                     }
-                }
-            }
-        }
-    } else if (warp == 8) {
-        // ===================== MMA issuer ==========================================================
-        const uint32_t idesc = umma_idesc_tf32(TC_M, BN);
-        const uint32_t b_ring = smem_u32(tc_smem);
-        uint32_t kbg = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int p = 0; p < a.npairs; ++p) {
-                for (int kbl = 0; kbl < KBp; ++kbl) {
-                    const int cc = kbl % nchunks;
-                    const int nvalid = min(TC_KB, Cs - cc * TC_KB);
-                    const int ksteps = (nvalid + 7) >> 3;
-                    const int s = kbg % TC_NST;
-                    const uint32_t round = kbg / TC_NST;
-                    const int b = kbg & 1;
-                    const uint32_t use = kbg >> 1;
-                    if (lane == 0) {
-                        mbar_wait(&a_full[s], round & 1);
-                        mbar_wait(&b_full[s], round & 1);
-                        if (use > 0) mbar_wait(&d_empty[b], (use - 1) & 1);
-                        tc_fence_after();
-                        const uint32_t d_addr = tmem + TC_DCOL0 + b * BN;
-                        const uint32_t a_hi = tmem + s * TC_ACOLS, a_lo = a_hi + 32;
-                        const uint32_t b_hi = b_ring + s * B_STAGE_BYTES, b_lo = b_hi + B_TILE_FLOATS * 4;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t koff = ks * 256;             // 2 core matrices of 128 B per k-step
-                            const uint64_t dBh = umma_desc(b_hi + koff, 128, 1024), dBl = umma_desc(b_lo + koff, 128, 1024);
-                            umma_tf32_ts(d_addr, a_hi + ks * 8, dBl, idesc, ks > 0 ? 1u : 0u);    // small terms first
-                            umma_tf32_ts(d_addr, a_lo + ks * 8, dBh, idesc, 1u);
-                            umma_tf32_ts(d_addr, a_hi + ks * 8, dBh, idesc, 1u);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i0 + i < mrem) {
+                            float val = acc[i0 + i] + prev[i];
+                            if (bias) val += __ldg(bias + m0 + i0 + i);
+                            if (a.relu_mode == 1) val = val > 0.f ? val : 0.f;
+                            else if (!(ref[i] > 0.f)) val = 0.f;
+                            outp[(long long)(i0 + i) * HWd] = val;
                         }
-                        umma_commit(&ab_free[s]);          // arrives when these MMAs have read the stage
-                        umma_commit(&d_full[b]);           // ... and when the block accumulator is complete
                     }
-                    __syncwarp();
-                    ++kbg;
                 }
             }
         }
     } else {
-        // ===================== B producer: bulk copies of the packed weight images ===================
-        uint32_t kbg = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile / n_jt;
-            for (int p = 0; p < a.npairs; ++p) {
-                const float* __restrict__ img = a.pack[p] + (long long)nt * KBp * 2 * B_TILE_FLOATS;
-                for (int kbl = 0; kbl < KBp; ++kbl) {
-                    const int s = kbg % TC_NST;
-                    const uint32_t round = kbg / TC_NST;
-                    if (lane == 0) {
-                        if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
-                        mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
-                        bulk_g2s(tc_smem + s * B_STAGE_BYTES, img + (long long)kbl * 2 * B_TILE_FLOATS, B_STAGE_BYTES,
-                                 &b_full[s]);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_MISC));
+        if (warp == TC_WARP_MMA) {
+            // ===================== MMA issuer ======================================================
+            // one thread; everything loop-invariant is hoisted, the per-k-block path is two barrier probes,
+            // <= 12 MMAs and two commits
+            const uint32_t idesc = umma_idesc_tf32(TC_M, BN);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);           // provably warp-uniform
+            const uint64_t desc0 = umma_desc(smem_u32(tc_smem), 128, 1024);      // stage 0, hi tile, k-step 0
+            const int last_ksteps = (Cs - (nchunks - 1) * TC_KB + 7) >> 3;
+            constexpr int NACC = tc_nacc(BN);
+            uint32_t kbg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int pt = 0; pt < a.npairs * KHW; ++pt) {
+                    for (int cc = 0; cc < nchunks; ++cc) {
+                        const int ksteps = cc == nchunks - 1 ? last_ksteps : TC_KB / 8;
+                        const int s = kbg % TC_NST;
+                        const uint32_t round = kbg / TC_NST;
+                        const int b = kbg & 1;
+                        const uint32_t use = kbg >> 1;
+                        if (lane == 0) tc_stamp(a.trace, 1, kbg, 0);
+                        mbar_wait(&a_full[s], round & 1);
+                        if (lane == 0) tc_stamp(a.trace, 1, kbg, 1);
+                        if (use > 0) mbar_wait(&d_empty[b], (use - 1) & 1);
+                        __syncwarp();
+                        tc_fence_after();
+                        if (lane == 0) tc_stamp(a.trace, 1, kbg, 2);
+                        const uint32_t d_addr = tmem_u + TC_DCOL0 + b * TC_DCOLS;
+                        const uint32_t a_hi = tmem_u + s * TC_ACOLS, a_lo = a_hi + 32;
+                        const uint64_t dBh = desc0 + (uint64_t)((s * B_STAGE_BYTES) >> 4);
+                        const uint64_t dBl = dBh + (uint64_t)((B_TILE_FLOATS * 4) >> 4);
+                        if (elect_one()) {
+                            // accumulator of (term, k-step): terms 0 = hi*lo, 1 = lo*hi (small, added first), 2 = hi*hi
+                            auto acc_of = [](int term, int ks) {
+                                return NACC == 6 ? term + 3 * (ks & 1) : NACC == 3 ? term : NACC == 2 ? (term == 2 ? 1 : 0) : 0;
+                            };
+#pragma unroll
+                            for (int ks = 0; ks < TC_KB / 8; ++ks) {
+                                if (ks < ksteps) {
+                                    const uint64_t ko = (uint64_t)(ks * 16);      // 2 core matrices of 128 B per k-step
+                                    const uint32_t fresh = NACC == 6 ? (ks >= 2) : (ks >= 1);   // accumulate onto this k-block's earlier k-steps
+                                    umma_tf32_ts(d_addr + acc_of(0, ks) * BN, a_hi + ks * 8, dBl + ko, idesc, fresh);
+                                    umma_tf32_ts(d_addr + acc_of(1, ks) * BN, a_lo + ks * 8, dBh + ko, idesc, NACC <= 2 ? 1u : fresh);
+                                    umma_tf32_ts(d_addr + acc_of(2, ks) * BN, a_hi + ks * 8, dBh + ko, idesc, NACC == 1 ? 1u : fresh);
+                                }
+                            }
+                            umma_commit(&ab_free[s]);      // arrives when these MMAs have read the stage
+                            umma_commit(&d_full[b]);       // ... and when the block accumulator is complete
+                        }
+                        __syncwarp();
+                        if (lane == 0) tc_stamp(a.trace, 1, kbg, 3);
+                        ++kbg;
                     }
-                    __syncwarp();
-                    ++kbg;
+                }
+            }
+        } else if (warp == TC_WARP_B) {
+            // ===================== B producer: bulk copies of the packed weight images ===============
+            uint32_t kbg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / n_jt;
+                for (int p = 0; p < a.npairs; ++p) {
+                    const float* __restrict__ img = a.pack[p] + (long long)nt * KBp * 2 * B_TILE_FLOATS;
+                    for (int kbl = 0; kbl < KBp; ++kbl) {
+                        const int s = kbg % TC_NST;
+                        const uint32_t round = kbg / TC_NST;
+                        if (lane == 0) {
+                            if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
+                            mbar_arrive_expect_tx(&b_full[s], B_STAGE_BYTES);
+                            bulk_g2s(tc_smem + s * B_STAGE_BYTES, img + (long long)kbl * 2 * B_TILE_FLOATS, B_STAGE_BYTES,
+                                     &b_full[s]);
+                        }
+                        __syncwarp();
+                        ++kbg;
+                    }
                 }
             }
         }
@@ -454,7 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == TC_WARP_MMA) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
@@ -471,6 +675,33 @@ static int launch_tc_t(cudaStream_t st, const ConvKArgs& a, long long J, int Cd)
     }
     const long long tiles = ((J + TC_M - 1) / TC_M) * ((Cd + BN - 1) / BN);
     const unsigned grid = (unsigned)std::min<long long>(tiles, kNumSMs);
+    static const bool want_trace = getenv("B2S_TC_TRACE") != nullptr;
+    static int traced = 0;
+    if (want_trace && traced < 6) {            // debug: synchronous launch + timeline dump of CTA 0
+        ++traced;
+        long long* d_tr = nullptr;
+        const size_t n = 4 * TC_TRACE_KB * 4;
+        cudaMalloc(&d_tr, n * sizeof(long long));
+        cudaMemset(d_tr, 0, n * sizeof(long long));
+        ConvKArgs b = a;
+        b.trace = d_tr;
+        conv_tc_kernel<BN, MODE><<<grid, TC_THREADS, smem, st>>>(b);
+        cudaStreamSynchronize(st);
+        std::vector<long long> h(n);
+        cudaMemcpy(h.data(), d_tr, n * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(d_tr);
+        long long t0 = 0;
+        for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+        fprintf(stderr, "TC trace BN=%d mode=%d J=%lld Cs=%d Cd=%d KHW=%d pairs=%d grid=%u (clocks since first stamp)\n", BN, MODE, J,
+                MODE == MODE_FWD ? a.g.Cin : a.g.Cout, Cd, a.g.KH * a.g.KW, a.npairs, grid);
+        for (int k = 0; k < TC_TRACE_KB; ++k) {
+            auto at = [&](int role, int slot) { long long v = h[((size_t)role * TC_TRACE_KB + k) * 4 + slot]; return v ? v - t0 : -1; };
+            if (at(1, 0) < 0) break;
+            fprintf(stderr, "  kb %2d  F: start %6lld loads %6lld adv %6lld | A: start %6lld stage %6lld st %6lld done %6lld | MMA: poll %6lld a_ok %6lld all_ok %6lld issued %6lld | D: poll %6lld full %6lld done %6lld\n",
+                    k, at(3, 0), at(3, 1), at(3, 2), at(0, 0), at(0, 1), at(0, 2), at(0, 3), at(1, 0), at(1, 1), at(1, 2), at(1, 3), at(2, 0), at(2, 1), at(2, 2));
+        }
+        return 1;
+    }
     conv_tc_kernel<BN, MODE><<<grid, TC_THREADS, smem, st>>>(a);
     return 1;
 }
@@ -495,9 +726,10 @@ int try_launch_conv_tc(int mode, cudaStream_t st, const ConvKArgs& a) {
     const int Cd = mode == MODE_FWD ? g.Cout : g.Cin;
     const int Cs = mode == MODE_FWD ? g.Cin : g.Cout;
     const long long J = (long long)g.batch * (mode == MODE_FWD ? g.OH * g.OW : g.H * g.W);
-    // automatic: wide layers with enough pixel tiles to be worth a tensor-core launch; narrow and
-    // classifier-sized problems stay on the CUDA-core kernels
-    if (g_tc_mode == 1 && (J < 1024 || Cd < 64 || Cs < 64)) return 0;
+    // automatic: enough pixel tiles to be worth a tensor-core launch; classifier-sized problems stay on the
+    // CUDA-core kernels
+    (void)Cs;
+    if (g_tc_mode == 1 && J < 1024) return 0;
     return mode == MODE_FWD ? launch_tc_mode<MODE_FWD>(st, a, J, Cd) : launch_tc_mode<MODE_DGRAD>(st, a, J, Cd);
 }
 

@@ -22,6 +22,7 @@ Differences that are deliberate:
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 import weakref
 from typing import Optional
@@ -66,6 +67,8 @@ class SpectralPlan:
                                             ctypes.byref(handle)), "b2s_plan_create")
         self.handle = handle
         self.dev_index = dev_index
+        if os.environ.get("B2S_NO_GRAPHS"):          # debugging aid: eager launches (kernel traces, sanitizers)
+            use_graphs = False
         _lib.check(self.lib.b2s_plan_set_graphs(self.handle, 1 if use_graphs else 0))
         self._bn_ptrs = None
         self.world = 1

@@ -103,6 +103,13 @@ class JetTapeOracle:
         self.stats = {}
         self.argmax = {}
         self.loss = None
+        # ReLU decisions: op index -> bool tensor, recorded by the order-0 forward.  `mask_override`
+        # (same keys) substitutes given decisions for the natural `pre-activation > 0`: used by the
+        # parity tests to condition the oracle on the decisions another implementation took where the
+        # pre-activation is within fp32 rounding of zero (tests/kinks.py).
+        self.masks = {}
+        self.preact = {}
+        self.mask_override = {}
         t0 = tape.tensors[0]
         self.view(self.fw, 0, 0).copy_(x.to(DT).reshape(self.B, *t0.shape))
 
@@ -116,6 +123,15 @@ class JetTapeOracle:
         for s in shape:
             n *= s
         return vec[off:off + n].view(*shape)
+
+    def decide(self, oi, pre):
+        """order-0 ReLU of op `oi`: records the pre-activation and the on/off decisions, returns the output"""
+        self.preact[oi] = pre.clone()
+        m = self.mask_override.get(oi)
+        if m is None:
+            m = pre > 0
+        self.masks[oi] = m
+        return pre * m
 
     # ---- passes --------------------------------------------------------------------------------
     def run(self, K, v=None):
@@ -153,12 +169,12 @@ class JetTapeOracle:
                 else:
                     y = torch.zeros_like(yout) if first else conv(xin[2], W) + 2 * conv(xin[1], V)
                 if relu:
-                    y = torch.relu(y) if K == 0 else y * (y0 > 0)
+                    y = self.decide(oi, y) if K == 0 else y * self.masks[oi]
                 yout.copy_(y)
             elif op.kind == T.OP_BN:
                 self.bn_forward(oi, op, K, first, relu)
             elif op.kind == T.OP_RELU:
-                yout.copy_(torch.relu(xin[0]) if K == 0 else xin[K] * (xin[0] > 0))
+                yout.copy_(self.decide(oi, xin[0]) if K == 0 else xin[K] * self.masks[oi])
             elif op.kind == T.OP_MAXPOOL:
                 kh, kw, sh, sw, ph, pw = op.geom
                 if K == 0:
@@ -220,7 +236,7 @@ class JetTapeOracle:
         xh = jmul(jsub(x, mu, K), r, K)
         y = jadd(jmul(gam, xh, K), bet, K)[K]
         if relu:
-            y = torch.relu(y) if K == 0 else y * (self.view(self.fw, 0, op.out) > 0)
+            y = self.decide(oi, y) if K == 0 else y * self.masks[oi]
         self.view(self.fw, K, op.out).copy_(y)
         if K == 0:
             var = self.stats[oi]["Q"][0] / N - (self.stats[oi]["T"][0] / N) ** 2
@@ -291,7 +307,7 @@ class JetTapeOracle:
                 cout = tp.tensors[op.out].shape[0]
                 kh, kw, sh, sw, ph, pw = op.geom
                 if relu:
-                    g[K].mul_(self.view(self.fw, 0, op.out) > 0)
+                    g[K].mul_(self.masks[oi])
                 W = self.wslice(self.w, op.w_off, (cout, cin, kh, kw))
                 V = self.wslice(self.v, op.w_off, (cout, cin, kh, kw))
                 wshape = (cout, cin, kh, kw)
@@ -314,7 +330,7 @@ class JetTapeOracle:
                 mu, r, gam, bet = self.bn_channel(oi, op, K, N)
                 xj = [x[0]] + ([torch.zeros_like(x[0])] * 2 if first else [x[1], x[2]])
                 xh = jmul(jsub(xj[:K + 1], mu, K), r, K)
-                mask = (self.view(self.fw, 0, op.out) > 0) if relu else 1.0
+                mask = self.masks[oi] if relu else 1.0
                 gm = [g[k] * mask for k in range(K + 1)]
                 st = self.stats[oi].setdefault("bw", {"G": [None] * 3, "X": [None] * 3})
                 st["G"][K] = gm[K].sum((0, 2, 3))
@@ -330,7 +346,7 @@ class JetTapeOracle:
                     emit(jmul(r, u, K)[K])
             elif op.kind == T.OP_RELU:
                 if not first:
-                    emit(g[K] * (x[0] > 0))
+                    emit(g[K] * self.masks[oi])
             elif op.kind == T.OP_MAXPOOL:
                 if not first:
                     idx = self.argmax[oi]
@@ -393,7 +409,7 @@ class JetTapeOracle:
                 cout = tp.tensors[op.out].shape[0]
                 kh, kw, sh, sw, ph, pw = op.geom
                 if relu:
-                    g.mul_(self.view(self.fw, 0, op.out) > 0)
+                    g.mul_(self.masks[oi])
                 W = self.wslice(self.w, op.w_off, (cout, cin, kh, kw))
                 wg = torch.nn.grad.conv2d_weight(x0, (cout, cin, kh, kw), g, (sh, sw), (ph, pw))
                 out[op.w_off:op.w_off + wg.numel()] += wg.reshape(-1)
@@ -405,7 +421,7 @@ class JetTapeOracle:
                 N = x0.shape[0] * x0.shape[2] * x0.shape[3]
                 mu, r, gam, bet = self.bn_channel(oi, op, 1, N)
                 r0, ga, gd = r[0], gam[0], gam[1]
-                mask = (self.view(self.fw, 0, op.out) > 0) if relu else 1.0
+                mask = self.masks[oi] if relu else 1.0
                 yb = self.view(self.bw, 0, op.out) * mask       # gO
                 h = self.view(self.bw, 1, op.out) * mask        # R ybar
                 xd = torch.zeros_like(x0) if first else self.view(self.fw, 1, op.inp)
@@ -429,7 +445,7 @@ class JetTapeOracle:
                     emit(r0 * ga * (gm - G / N - xh * X / N) + dmu / N - dr * r3 * c / N)
             elif op.kind == T.OP_RELU:
                 if not first:
-                    emit(g * (x0 > 0))
+                    emit(g * self.masks[oi])
             elif op.kind == T.OP_MAXPOOL:
                 if not first:
                     idx = self.argmax[oi]
