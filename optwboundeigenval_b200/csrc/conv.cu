@@ -592,6 +592,14 @@ int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const floa
     const double macs = (double)g.batch * g.OH * g.OW * g.Cout * g.Cin * g.KH * g.KW;
     ProfScope prof("conv_wgrad", 2.0 * macs * npairs,
                    4.0 * npairs * ((double)g.batch * g.Cin * g.H * g.W + (double)g.batch * g.Cout * g.OH * g.OW), st);
+    {
+        const int rc = try_launch_wgrad_tc(st, a);           // tcgen05 path
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            B2S_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const int Ncol = g.Cin * g.KH * g.KW;
     const long long J = (long long)g.batch * g.OH * g.OW;
     constexpr int BK = 32;

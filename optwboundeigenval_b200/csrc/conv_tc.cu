@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "conv_args.h"
+#include "tc_common.cuh"
 
 namespace b2s {
 
@@ -45,134 +46,6 @@ static int initial_tc_mode() {
 static int g_tc_mode = initial_tc_mode();
 void set_tc_mode(int mode) { g_tc_mode = mode; }
 int get_tc_mode() { return g_tc_mode; }
-
-constexpr int TC_M = 128;        // pixels per tile (UMMA M, cta_group::1)
-constexpr int TC_KB = 32;        // k per k-block = 4 UMMA k-steps of 8 (tf32)
-constexpr int TC_NST = 3;        // pipeline stages (A in TMEM, B in shared memory)
-constexpr int TC_ACOLS = 64;     // TMEM columns per A stage: 32 hi + 32 lo
-constexpr int TC_DCOL0 = TC_NST * TC_ACOLS;    // first accumulator column
-constexpr int TC_DCOLS = (512 - TC_DCOL0) / 2; // columns of one of the two accumulator buffers (160)
-// Consecutive tcgen05.mma into the SAME accumulator serialise on its ~90-clock read-modify-write latency
-// (measured: 12 dependent MMAs take ~1100 clocks whether N is 16 or 128).  Narrow tiles therefore spread
-// the three 3xTF32 terms (hi*lo, lo*hi, hi*hi) -- and for BN = 16 also odd / even k-steps -- over
-// independent accumulators inside the buffer; the drain adds them up.
-__host__ __device__ constexpr int tc_nacc(int BN) { return 6 * BN <= TC_DCOLS ? 6 : 3 * BN <= TC_DCOLS ? 3 : 2 * BN <= TC_DCOLS ? 2 : 1; }
-constexpr int TC_THREADS = 512;  // four warpgroups: 2 x A transform, drain, {MMA issuer, B producer, 2 idle warps}
-constexpr int TC_WARP_MMA = 12;
-constexpr int TC_WARP_B = 13;
-// registers per thread after the role split (setmaxnreg): 128 (launch) for the transform warpgroups,
-// TC_REGS_DRAIN for the warpgroup that holds up to 128 accumulators per thread, TC_REGS_MISC for the rest;
-// 128 * (128 + 128 + 208 + 40) <= 64 K registers
-constexpr int TC_REGS_DRAIN = 208;
-constexpr int TC_REGS_MISC = 40;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (between the two 16 B K-chunks of a
-//   k-step = adjacent core matrices along K), [32,46) stride byte offset >> 4 (between 8-row groups),
-//   [46,48) version = 1 (Blackwell), [61,64) layout type = 0.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a/b_format TF32 = 2 @
-// [7,10)/[10,13), a/b major K = 0 @ 15/16, n_dim = N >> 3 @ [17,23), m_dim = M >> 4 @ [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]^T   (SM100_MMA_TF32_TS)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    return done;
-}
-// bounded wait: a protocol error must become a trap (launch failure), never a hang.  The clock is only
-// read once the first probe has failed (the issuing thread's fast path is a single try_wait).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    if (mbar_try(addr, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try(addr, parity)) {
-        if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t to_tf32_bits(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-// one lane of a converged warp; operands computed warp-uniformly OUTSIDE the elected branch stay in uniform
-// registers, so each tcgen05.mma is a single UTCHMMA (a branch on lane == 0 makes the compiler wrap every
-// MMA in an R2UR broadcast loop: ~90 clocks per instruction)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: flat parameter vector -> per (op, mode) images of every k-block's B tile
@@ -359,8 +232,13 @@ struct TcCursor {
 
 // debug timeline: trace[(role * TC_TRACE_KB + kbg) * 4 + slot] = clock64(), CTA 0, first TC_TRACE_KB k-blocks
 constexpr int TC_TRACE_KB = 48;
+// (compiled in only with -DB2S_TC_TRACE_ENABLED: `B2S_BUILD_TRACE=1 python -m optwboundeigenval_b200.build --force`)
 __device__ __forceinline__ void tc_stamp(long long* trace, int role, uint32_t kbg, int slot) {
+#ifdef B2S_TC_TRACE_ENABLED
     if (trace && blockIdx.x == 0 && kbg < TC_TRACE_KB) trace[((size_t)role * TC_TRACE_KB + kbg) * 4 + slot] = clock64();
+#else
+    (void)trace; (void)role; (void)kbg; (void)slot;
+#endif
 }
 
 // split one k-block of A values and hand it to the tensor core: wait for the TMEM stage, tcgen05.st

@@ -1,0 +1,325 @@
+// conv_tc_wgrad.cu -- tcgen05 / TMEM weight-gradient contraction of the Conv2d / Linear jets (sm_100a).
+//
+//   Wbar[co][ci][ky][kx] += sum_p scale_p * sum_{n,oy,ox} g_p[n,co,oy,ox] * x_p[n,ci,oy+ky-ph,ox+kx-pw]
+//
+// (order K of a layer: up to three (x_j, g_{K-j}) pairs with binomial scales; this is
+// the Hv slice of the layer for K = 1.)  GEMM view: the contraction index K is the OUTPUT PIXEL, which is
+// the contiguous dimension of both NCHW operands, so both are K-major as they lie in memory:
+//   A [128 rows = (tap, ci)] x [32 pixels]   the input, shifted per tap, zero outside the image
+//   B [BN  rows = co]        x [32 pixels]   the output adjoint
+//   D [128 x BN] in TMEM, one fresh accumulator per 32-pixel k-block, drained into fp32 registers
+//   (same fp32-accurate 3xTF32 scheme and the same reason as conv_tc.cu).
+// A warp instruction loads an [8 rows x 4 pixel-groups] patch with 128-bit accesses (64 contiguous bytes per
+// row), splits it hi/lo in registers and stores it with conflict-free 128-bit shared-memory stores straight
+// into the canonical K-major core-matrix layout; a tap with a horizontal shift adds one scalar load per
+// patch for the element that crosses the 16-byte boundary.  fence.proxy.async hands the stage to the
+// tensor core (SS MMA).  The grid splits the pixel range (split-K) so that all 148 SMs work; each CTA
+// atomically adds its partial tile into the flat gradient vector.
+//
+// Eligible: stride 1, horizontal shift in {-1, 0, +1}, OW and W multiples of 4, Cin a multiple of 8.
+// Everything else stays on the CUDA-core kernel (conv.cu).
+#include <algorithm>
+
+#include "conv_args.h"
+#include "tc_common.cuh"
+
+namespace b2s {
+
+constexpr int WG_NST = 3;                      // shared-memory stages
+constexpr int WG_A_FLOATS = TC_M * TC_KB;      // one of hi / lo
+
+template <int BN>
+struct WgSmem {
+    static constexpr int B_FLOATS = BN * TC_KB;
+    static constexpr int STAGE_FLOATS = 2 * WG_A_FLOATS + 2 * B_FLOATS;
+    static constexpr size_t BYTES = (size_t)WG_NST * STAGE_FLOATS * sizeof(float) + 256;
+};
+
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+    hi.x = __uint_as_float(to_tf32_bits(v.x)); lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & 0xffffe000u);
+    hi.y = __uint_as_float(to_tf32_bits(v.y)); lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & 0xffffe000u);
+    hi.z = __uint_as_float(to_tf32_bits(v.z)); lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & 0xffffe000u);
+    hi.w = __uint_as_float(to_tf32_bits(v.w)); lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & 0xffffe000u);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, const int ksplit) {
+    extern __shared__ __align__(1024) uint8_t wg_smem[];
+    using S = WgSmem<BN>;
+    float* stages = reinterpret_cast<float*>(wg_smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wg_smem + (size_t)WG_NST * S::STAGE_FLOATS * sizeof(float));
+    uint64_t* ab_full = bars;                  // [NST] the 128 transform threads of the owning group
+    uint64_t* ab_free = bars + WG_NST;         // [NST] tcgen05.commit
+    uint64_t* d_full = bars + 2 * WG_NST;      // [2]
+    uint64_t* d_empty = d_full + 2;            // [2]   128 drain threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+    const ConvGeom& g = a.g;
+    const int KHW = g.KH * g.KW;
+    const int OHW = g.OH * g.OW, HW = g.H * g.W;
+    const long long J = (long long)g.batch * OHW;
+    const int nkb = (int)((J + TC_KB - 1) / TC_KB);
+    const int Mrows = KHW * g.Cin;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mt = blockIdx.x % mtiles;
+    const int nt = (blockIdx.x / mtiles) % ntiles;
+    const int ksl = blockIdx.x / (mtiles * ntiles);
+    const int per = (nkb + ksplit - 1) / ksplit;
+    const int kb0 = ksl * per;
+    const int nloc = max(0, min(nkb, kb0 + per) - kb0);         // k-blocks of this CTA per pair
+    const int total = a.npairs * nloc;
+
+    if (tid == 0) {
+        for (int s = 0; s < WG_NST; ++s) {
+            mbar_init(&ab_full[s], 128);
+            mbar_init(&ab_free[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d_full[b], 1);
+            mbar_init(&d_empty[b], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_WARP_MMA) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ===================== operand transform: global -> registers (split) -> shared memory =========
+        const int grp = warp >> 2, wq = warp & 3;
+        const int l8 = lane & 7, l4 = lane >> 3;
+        for (int i = grp; i < total; i += 2) {
+            const int p = i / nloc;
+            const int kb = kb0 + (i - p * nloc);
+            const int s = i % WG_NST;
+            const uint32_t round = i / WG_NST;
+            float* Ahi = stages + (size_t)s * S::STAGE_FLOATS;
+            float* Alo = Ahi + WG_A_FLOATS;
+            float* Bhi = Alo + WG_A_FLOATS;
+            float* Blo = Bhi + S::B_FLOATS;
+            // the two 4-pixel groups of this lane inside the k-block: k-groups l4 and l4 + 4
+            int n_[2], oy_[2], ox_[2], rem_[2];
+            bool pv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long j = (long long)kb * TC_KB + (h * 4 + l4) * 4;
+                pv[h] = j < J;
+                const unsigned jj = pv[h] ? (unsigned)j : 0u;
+                n_[h] = jj / (unsigned)OHW;
+                rem_[h] = jj - n_[h] * OHW;
+                oy_[h] = rem_[h] / g.OW;
+                ox_[h] = rem_[h] - oy_[h] * g.OW;
+            }
+            const float* __restrict__ xp = a.act[p];
+            const float* __restrict__ gp = a.wt[p];
+            // ---- issue every load of this warp's share of the stage
+            float4 ca[4][2];
+            float ea[4][2];
+            int dxs[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rg = wq * 4 + q;                      // 8-row group of the A tile
+                const int m0 = mt * TC_M + rg * 8;              // first row: all 8 rows share the tap (Cin % 8 == 0)
+                const int t = m0 / g.Cin;
+                const int ci = m0 - t * g.Cin + l8;
+                const int ky = t / g.KW, kx = t - ky * g.KW;
+                const int dy = ky - g.ph, dx = kx - g.pw;
+                dxs[q] = dx;
+                const bool row_ok = m0 < Mrows;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int sy = oy_[h] + dy;
+                    const bool ok = row_ok && pv[h] && sy >= 0 && sy < g.H;
+                    const float* ptr = xp + (long long)n_[h] * g.in_sstride + (long long)ci * HW + sy * g.W + ox_[h];
+                    ca[q][h] = ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float e = 0.f;
+                    if (dx < 0) { if (ok && ox_[h] > 0) e = __ldg(ptr - 1); }
+                    else if (dx > 0) { if (ok && ox_[h] + 4 < g.W) e = __ldg(ptr + 4); }
+                    ea[q][h] = e;
+                }
+            }
+            constexpr int NB = BN / 16;                          // B patches of this warp
+            float4 cb[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int idx = wq + 4 * u;
+                const int rgB = idx >> 1, h = idx & 1;
+                const int co = nt * BN + rgB * 8 + l8;
+                const bool ok = pv[h] && co < g.Cout;
+                const float* ptr = gp + (long long)n_[h] * g.out_sstride + (long long)co * OHW + rem_[h];
+                cb[u] = ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // ---- the stage must have been read by the MMAs of its previous use
+            if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rg = wq * 4 + q;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float4 v = ca[q][h];
+                    if (dxs[q] < 0) v = make_float4(ea[q][h], v.x, v.y, v.z);
+                    else if (dxs[q] > 0) v = make_float4(v.y, v.z, v.w, ea[q][h]);
+                    float4 hi, lo;
+                    split4(v, hi, lo);
+                    const int o = rg * 256 + h * 128 + lane * 4;       // ((rg*8 + kgroup) * 32) + (row%8)*4, kgroup = h*4 + lane/8
+                    *reinterpret_cast<float4*>(Ahi + o) = hi;
+                    *reinterpret_cast<float4*>(Alo + o) = lo;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int idx = wq + 4 * u;
+                const int rgB = idx >> 1, h = idx & 1;
+                float4 hi, lo;
+                split4(cb[u], hi, lo);
+                const int o = rgB * 256 + h * 128 + lane * 4;
+                *reinterpret_cast<float4*>(Bhi + o) = hi;
+                *reinterpret_cast<float4*>(Blo + o) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the tensor core
+            mbar_arrive(&ab_full[s]);
+        }
+    } else if (warp < 12) {
+        // ===================== drain + epilogue ======================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_DRAIN));
+        const int q = warp - 8;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        constexpr int NACC = tc_nacc(BN) > 3 ? 3 : tc_nacc(BN);
+        float acc[BN];
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+        for (int i = 0; i < total; ++i) {
+            const float sc = a.scale[i / nloc];
+            const int b = i & 1;
+            mbar_wait(&d_full[b], (i >> 1) & 1);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t d0 = lane_addr + TC_DCOL0 + b * TC_DCOLS;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[NACC][16];
+#pragma unroll
+                for (int q2 = 0; q2 < NACC; ++q2) tmem_ld16(d0 + q2 * BN + c0, v[q2]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float d = __uint_as_float(v[0][e]);
+                    if (NACC >= 2) d += __uint_as_float(v[1][e]);
+                    if (NACC >= 3) d += __uint_as_float(v[2][e]);
+                    acc[c0 + e] = fmaf(d, sc, acc[c0 + e]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&d_empty[b]);
+        }
+        const int m = mt * TC_M + r;
+        if (total > 0 && m < Mrows) {
+            const int t = m / g.Cin, ci = m - t * g.Cin;
+            float* __restrict__ wrow = a.out + (long long)ci * KHW + t;
+#pragma unroll
+            for (int i = 0; i < BN; ++i) {
+                const int co = nt * BN + i;
+                if (co < g.Cout) atomicAdd(wrow + (long long)co * g.Cin * KHW, acc[i]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_MISC));
+        if (warp == TC_WARP_MMA) {
+            // ===================== MMA issuer ======================================================
+            const uint32_t idesc = umma_idesc_tf32(TC_M, BN);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint64_t desc0 = umma_desc(smem_u32(wg_smem), 128, 1024);      // stage 0, A hi, k-step 0
+            constexpr int NACC = tc_nacc(BN) > 3 ? 3 : tc_nacc(BN);
+            constexpr uint32_t STAGE16 = (uint32_t)(S::STAGE_FLOATS * 4) >> 4;
+            constexpr uint32_t A16 = (uint32_t)(WG_A_FLOATS * 4) >> 4, B16 = (uint32_t)(S::B_FLOATS * 4) >> 4;
+            for (int i = 0; i < total; ++i) {
+                const int s = i % WG_NST;
+                const uint32_t round = i / WG_NST;
+                const int b = i & 1;
+                const uint32_t use = i >> 1;
+                mbar_wait(&ab_full[s], round & 1);
+                if (use > 0) mbar_wait(&d_empty[b], (use - 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+                const uint32_t d_addr = tmem_u + TC_DCOL0 + b * TC_DCOLS;
+                const uint64_t dAh = desc0 + (uint64_t)(s * STAGE16), dAl = dAh + A16;
+                const uint64_t dBh = dAl + A16, dBl = dBh + B16;
+                if (elect_one()) {
+                    auto acc_of = [](int term) { return NACC == 3 ? term : NACC == 2 ? (term == 2 ? 1 : 0) : 0; };
+#pragma unroll
+                    for (int ks = 0; ks < TC_KB / 8; ++ks) {
+                        const uint64_t ko = (uint64_t)(ks * 16);
+                        const uint32_t fresh = ks >= 1;
+                        umma_tf32_ss(d_addr + acc_of(0) * BN, dAh + ko, dBl + ko, idesc, fresh);
+                        umma_tf32_ss(d_addr + acc_of(1) * BN, dAl + ko, dBh + ko, idesc, NACC <= 2 ? 1u : fresh);
+                        umma_tf32_ss(d_addr + acc_of(2) * BN, dAh + ko, dBh + ko, idesc, NACC == 1 ? 1u : fresh);
+                    }
+                    umma_commit(&ab_free[s]);
+                    umma_commit(&d_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_WARP_MMA) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+template <int BN>
+static int launch_wg_t(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntiles, int ksplit) {
+    constexpr size_t smem = WgSmem<BN>::BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+        attr_set = true;
+    }
+    conv_tc_wgrad_kernel<BN><<<mtiles * ntiles * ksplit, TC_THREADS, smem, st>>>(a, mtiles, ntiles, ksplit);
+    return 1;
+}
+
+// Returns 1 when the tensor-core kernel was launched, 0 when the layer is not eligible, <0 on error.
+int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a) {
+    const int mode = get_tc_mode();
+    if (mode == 0) return 0;
+    const ConvGeom& g = a.g;
+    const long long J = (long long)g.batch * g.OH * g.OW;
+    if (g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || (g.Cin & 7) || g.KW - 1 - g.pw > 1 || g.pw > 1) return 0;
+    if (((uintptr_t)a.out & 3) != 0 || (g.in_sstride & 3) || (g.out_sstride & 3)) return 0;
+    for (int p = 0; p < a.npairs; ++p)
+        if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) return 0;
+    if (J >= (1LL << 31)) return 0;
+    if (mode == 1 && J < 1024) return 0;
+    const int BN = tc_choose_bn(g.Cout);
+    const int mtiles = (g.KH * g.KW * g.Cin + TC_M - 1) / TC_M;
+    const int ntiles = (g.Cout + BN - 1) / BN;
+    const int nkb = (int)((J + TC_KB - 1) / TC_KB);
+    int ksplit = std::max(1, kNumSMs / (mtiles * ntiles));
+    ksplit = std::min(ksplit, nkb);
+    switch (BN) {
+    case 16: return launch_wg_t<16>(st, a, mtiles, ntiles, ksplit);
+    case 32: return launch_wg_t<32>(st, a, mtiles, ntiles, ksplit);
+    case 48: return launch_wg_t<48>(st, a, mtiles, ntiles, ksplit);
+    case 64: return launch_wg_t<64>(st, a, mtiles, ntiles, ksplit);
+    case 96: return launch_wg_t<96>(st, a, mtiles, ntiles, ksplit);
+    default: return launch_wg_t<128>(st, a, mtiles, ntiles, ksplit);
+    }
+}
+
+}  // namespace b2s

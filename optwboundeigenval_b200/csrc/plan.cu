@@ -12,6 +12,7 @@
 // replayed (one graph launch per HVP instead of the reference's per-op autograd dispatch).
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -132,6 +133,7 @@ struct b2s_plan {
     float* out_corr = nullptr;        // its parameter-space result
     bool bn_exact_third_order = false;
     bool bn_fused = true;             // statistics+apply in one cooperative launch (single GPU)
+    bool wgrad_side = true;           // weight-gradient contractions on the side stream
     std::vector<float*> bn_rm, bn_rv;
 
     // max pool
@@ -349,6 +351,7 @@ static int forward(b2s_plan* p, int K) {
 // before the pass ends.  Fork it onto the side stream (ordered after everything enqueued so far on
 // the main stream) so the adjoint chain  dgrad -> BN backward -> dgrad ...  does not wait for it.
 static int fork_side(b2s_plan* p) {
+    if (!p->wgrad_side) return 0;
     B2S_CUDA(cudaEventRecord(p->ev_fork, p->stream));
     B2S_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     p->side_used = true;
@@ -393,9 +396,10 @@ static int backward(b2s_plan* p, int K) {
             if (!first && K >= 1) { a_[np] = x[1]; b_[np] = gk[K - 1]; sc[np] = K == 2 ? 2.f : 1.f; ++np; }
             if (!first && K == 2) { a_[np] = x[2]; b_[np] = gk[0]; sc[np] = 1.f; ++np; }
             B2S_TRY(fork_side(p));
-            B2S_TRY(launch_conv_wgrad(p->side, g, np, a_, b_, sc, p->out32[K] + op.w_off));
+            cudaStream_t ws = p->wgrad_side ? p->side : st;
+            B2S_TRY(launch_conv_wgrad(ws, g, np, a_, b_, sc, p->out32[K] + op.w_off));
             if (op.b_off >= 0)
-                B2S_TRY(launch_bias_grad(p->side, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
+                B2S_TRY(launch_bias_grad(ws, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
                                          p->out32[K] + op.b_off));
             if (!first) {
                 np = 0;
@@ -473,9 +477,10 @@ static int backward_correction(b2s_plan* p) {
             const float* W = p->params + op.w_off;
             const float one = 1.f;
             B2S_TRY(fork_side(p));
-            B2S_TRY(launch_conv_wgrad(p->side, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
+            cudaStream_t ws = p->wgrad_side ? p->side : st;
+            B2S_TRY(launch_conv_wgrad(ws, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
             if (op.b_off >= 0)
-                B2S_TRY(launch_bias_grad(p->side, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
+                B2S_TRY(launch_bias_grad(ws, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
             if (!first) {
                 const float* pk = tc_image(p, oi, MODE_DGRAD, W);
                 B2S_TRY(launch_conv_dgrad(st, g, 1, &gc, &W, &one, tptr(p, p->bw, 2, op.in), acc, &pk));
@@ -675,6 +680,8 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     B2S_CUDA(cudaSetDevice(device));
     b2s_plan* p = new b2s_plan();
     p->device = device;
+    if (const char* e = getenv("B2S_BN_FUSED")) p->bn_fused = atoi(e) != 0;      // experiment switch
+    if (const char* e = getenv("B2S_WGRAD_SIDE")) p->wgrad_side = atoi(e) != 0;
     p->tensors.assign(tensors, tensors + n_tensors);
     p->ops.assign(ops, ops + n_ops);
     p->buf_elems.assign(buf_elems, buf_elems + n_bufs);

@@ -335,9 +335,10 @@ def test_kfac_preconditioned_variant_matches_reference_golden(name, kind, alpha,
 
 
 def test_tensor_core_path_matches_cuda_core_path_and_oracle():
-    """tcgen05 / TMEM 3xTF32 contractions (conv_tc.cu) against the fp32 CUDA-core kernels and the CPU oracle on
-    a network with wide layers: 3x3 and 1x1 convs with and without bias, ragged channel counts, a pixel count
-    that is not a multiple of the 128-row tile."""
+    """tcgen05 / TMEM 3xTF32 contractions (conv_tc.cu forward / input-adjoint, conv_tc_wgrad.cu weight gradient)
+    against the fp32 CUDA-core kernels and the CPU oracle on a network with wide layers: 3x3 and 1x1 convs with
+    and without bias, ragged channel counts, a pixel count (5 x 12 x 12 = 720) that is neither a multiple of the
+    128-pixel tile nor of the 32-pixel k-block of the weight-gradient kernel."""
     import torch.nn as nn
     from optwboundeigenval_b200 import _lib
     from optwboundeigenval_b200.hvp_operator import B200HVPOperator, clear_plans
@@ -352,19 +353,19 @@ def test_tensor_core_path_matches_cuda_core_path_and_oracle():
             self.bn = nn.BatchNorm2d(136)
             self.c3 = nn.Conv2d(136, 64, 1)
             self.pool = nn.MaxPool2d(2)
-            self.fc = nn.Linear(64 * 5 * 5, 7)
+            self.fc = nn.Linear(64 * 6 * 6, 7)
 
         def forward(self, x):
             h = torch.relu(self.c1(x))
             h = torch.relu(self.bn(self.c2(h)))
             h = self.pool(torch.relu(self.c3(h)))
-            return self.fc(h.view(-1, 64 * 25))
+            return self.fc(h.view(-1, 64 * 36))
 
     model = Wide().train()
     loss = nn.CrossEntropyLoss()
     g = torch.Generator().manual_seed(6)
-    x = torch.randn(6, 5, 10, 10, generator=g)          # 600 pixels: 4 full tiles + a ragged one
-    y = torch.randint(0, 7, (6,), generator=g)
+    x = torch.randn(5, 5, 12, 12, generator=g)          # 720 pixels: 5 full tiles + a ragged one
+    y = torch.randint(0, 7, (5,), generator=g)
     P = sum(p.numel() for p in model.parameters())
     v = torch.randn(P, generator=g, dtype=torch.float64)
     v /= v.norm()
