@@ -12,6 +12,8 @@
 // elementwise apply (grid = C x chunks).  Both are HBM/L2-bandwidth bound.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b2s {
@@ -328,6 +330,32 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float
     bn_bwd_apply_body<K, VEC>(a, ps);
 }
 
+// Small per-channel extents (every DenseNet3 layer): ONE CTA per channel does statistics, then apply, with a
+// block barrier in between -- no grid-wide barrier, no cooperative launch (which has to wait until the whole
+// grid fits beside whatever the weight-gradient stream is running), the second read hits L1/L2.
+template <int K, int VEC>
+__global__ void __launch_bounds__(1024) bn_fwd_chan_kernel(const BnArgs a, int do_stats) {
+    if (do_stats) bn_fwd_stats_body<K, VEC>(a);
+    __threadfence();
+    __syncthreads();
+    bn_fwd_apply_body<K, VEC>(a);
+}
+template <int K, int VEC>
+__global__ void __launch_bounds__(1024) bn_bwd_chan_kernel(const BnArgs a, float ps) {
+    bn_bwd_stats_body<K, VEC>(a);
+    __threadfence();
+    __syncthreads();
+    bn_bwd_apply_body<K, VEC>(a, ps);
+}
+// per-channel CTA form applies when a channel's extent is small enough for one CTA and there are enough
+// channels to occupy the machine; returns the block size or 0
+static inline int bn_chan_block(const BnArgs& a, int vec) {
+    const long long per_chan = (long long)a.batch * a.HW / vec;      // chunks per channel
+    static const long long limit = getenv("B2S_BN_CHAN_MAX") ? atoll(getenv("B2S_BN_CHAN_MAX")) : 1024;
+    if (a.C < 16 || per_chan > limit) return 0;
+    return per_chan >= 4096 ? 1024 : per_chan >= 1024 ? 512 : 256;
+}
+
 template <typename F>
 static dim3 coop_grid(const BnArgs& a, int vec, F kernel, bool* fits) {
     int per_sm = 0;
@@ -387,6 +415,13 @@ int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stat
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_fwd_fused", 16.0 * elems, 4.0 * elems * (2 * order + 3), st);
     const int vec = bn_vec(a);
+    if (const int blk = bn_chan_block(a, vec)) {
+#define CALL(K_, V_) bn_fwd_chan_kernel<K_, V_><<<dim3(a.C, 1), blk, 0, st>>>(a, do_stats)
+        B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
+        B2S_LAUNCH_CHECK();
+        return 0;
+    }
 #define CALL(K_, V_) return launch_fwd_fused_t<K_, V_>(st, a, do_stats)
     B2S_BN_DISPATCH(order, vec, CALL);
 #undef CALL
@@ -396,6 +431,14 @@ int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_bwd_fused", 16.0 * elems, 4.0 * elems * (4 * order + 7), st);
     const int vec = bn_vec(a);
+    if (const int blk = bn_chan_block(a, vec)) {
+        const float ps = a.pgrad_scale;
+#define CALL(K_, V_) bn_bwd_chan_kernel<K_, V_><<<dim3(a.C, 1), blk, 0, st>>>(a, ps)
+        B2S_BN_DISPATCH(order, vec, CALL);
+#undef CALL
+        B2S_LAUNCH_CHECK();
+        return 0;
+    }
 #define CALL(K_, V_) return launch_bwd_fused_t<K_, V_>(st, a)
     B2S_BN_DISPATCH(order, vec, CALL);
 #undef CALL

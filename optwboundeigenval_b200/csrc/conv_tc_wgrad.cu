@@ -16,9 +16,10 @@
 // tensor core (SS MMA).  The grid splits the pixel range (split-K) so that all 148 SMs work; each CTA
 // atomically adds its partial tile into the flat gradient vector.
 //
-// Eligible: stride 1, horizontal shift in {-1, 0, +1}, OW and W multiples of 4, Cin a multiple of 8.
+// Eligible: stride 1, horizontal shift in {-1, 0, +1}, OW and W multiples of 4.
 // Everything else stays on the CUDA-core kernel (conv.cu).
 #include <algorithm>
+#include <cstdlib>
 
 #include "conv_args.h"
 #include "tc_common.cuh"
@@ -44,7 +45,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, const int ksplit) {
+conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, const int ksplit, const int swapped) {
     extern __shared__ __align__(1024) uint8_t wg_smem[];
     using S = WgSmem<BN>;
     float* stages = reinterpret_cast<float*>(wg_smem);
@@ -88,6 +89,12 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    {   // row groups past the last row of the A tile are never written again: zero the stages once
+        float4* z = reinterpret_cast<float4*>(wg_smem);
+        const int n4 = WG_NST * S::STAGE_FLOATS / 4;
+        for (int i = tid; i < n4; i += TC_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -97,6 +104,34 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
         // ===================== operand transform: global -> registers (split) -> shared memory =========
         const int grp = warp >> 2, wq = warp & 3;
         const int l8 = lane & 7, l4 = lane >> 3;
+        // per-lane constants of this warp's four A row groups: channel-plane offset (+ vertical tap shift),
+        // vertical / horizontal shift, row validity.  A row group that lies entirely past the last row is
+        // never touched (its shared memory was zeroed once at kernel start).
+        int rowoff[4], dyv[4], dxv[4];
+        bool rok[4], gok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int m0 = mt * TC_M + (wq * 4 + q) * 8;
+            const int m = m0 + l8;
+            gok[q] = m0 < Mrows;
+            rok[q] = m < Mrows;
+            const int t = rok[q] ? m / g.Cin : 0;
+            const int ci = rok[q] ? m - t * g.Cin : 0;
+            const int ky = t / g.KW, kx = t - ky * g.KW;
+            dyv[q] = ky - g.ph;
+            dxv[q] = kx - g.pw;
+            rowoff[q] = ci * HW + dyv[q] * g.W;
+        }
+        constexpr int NB = BN / 16;                          // B patches of this warp
+        int boff[NB];
+        bool bok[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int idx = wq + 4 * u;
+            const int co = nt * BN + (idx >> 1) * 8 + l8;
+            bok[u] = co < g.Cout;
+            boff[u] = bok[u] ? co * OHW : 0;
+        }
         for (int i = grp; i < total; i += 2) {
             const int p = i / nloc;
             const int kb = kb0 + (i - p * nloc);
@@ -107,68 +142,60 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
             float* Bhi = Alo + WG_A_FLOATS;
             float* Blo = Bhi + S::B_FLOATS;
             // the two 4-pixel groups of this lane inside the k-block: k-groups l4 and l4 + 4
-            int n_[2], oy_[2], ox_[2], rem_[2];
+            int oy_[2], ox_[2];
+            long long xo[2], go[2];
             bool pv[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const long long j = (long long)kb * TC_KB + (h * 4 + l4) * 4;
                 pv[h] = j < J;
                 const unsigned jj = pv[h] ? (unsigned)j : 0u;
-                n_[h] = jj / (unsigned)OHW;
-                rem_[h] = jj - n_[h] * OHW;
-                oy_[h] = rem_[h] / g.OW;
-                ox_[h] = rem_[h] - oy_[h] * g.OW;
+                const unsigned n = jj / (unsigned)OHW;
+                const unsigned rem = jj - n * OHW;
+                oy_[h] = rem / g.OW;
+                ox_[h] = rem - oy_[h] * g.OW;
+                xo[h] = (long long)n * g.in_sstride + oy_[h] * g.W + ox_[h];
+                go[h] = (long long)n * g.out_sstride + rem;
             }
             const float* __restrict__ xp = a.act[p];
             const float* __restrict__ gp = a.wt[p];
             // ---- issue every load of this warp's share of the stage
             float4 ca[4][2];
             float ea[4][2];
-            int dxs[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int rg = wq * 4 + q;                      // 8-row group of the A tile
-                const int m0 = mt * TC_M + rg * 8;              // first row: all 8 rows share the tap (Cin % 8 == 0)
-                const int t = m0 / g.Cin;
-                const int ci = m0 - t * g.Cin + l8;
-                const int ky = t / g.KW, kx = t - ky * g.KW;
-                const int dy = ky - g.ph, dx = kx - g.pw;
-                dxs[q] = dx;
-                const bool row_ok = m0 < Mrows;
+                if (!gok[q]) continue;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int sy = oy_[h] + dy;
-                    const bool ok = row_ok && pv[h] && sy >= 0 && sy < g.H;
-                    const float* ptr = xp + (long long)n_[h] * g.in_sstride + (long long)ci * HW + sy * g.W + ox_[h];
+                    const int sy = oy_[h] + dyv[q];
+                    const bool ok = rok[q] && pv[h] && sy >= 0 && sy < g.H;
+                    const float* ptr = xp + xo[h] + rowoff[q];
                     ca[q][h] = ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float e = 0.f;
-                    if (dx < 0) { if (ok && ox_[h] > 0) e = __ldg(ptr - 1); }
-                    else if (dx > 0) { if (ok && ox_[h] + 4 < g.W) e = __ldg(ptr + 4); }
+                    if (dxv[q] < 0) { if (ok && ox_[h] > 0) e = __ldg(ptr - 1); }
+                    else if (dxv[q] > 0) { if (ok && ox_[h] + 4 < g.W) e = __ldg(ptr + 4); }
                     ea[q][h] = e;
                 }
             }
-            constexpr int NB = BN / 16;                          // B patches of this warp
             float4 cb[NB];
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
-                const int idx = wq + 4 * u;
-                const int rgB = idx >> 1, h = idx & 1;
-                const int co = nt * BN + rgB * 8 + l8;
-                const bool ok = pv[h] && co < g.Cout;
-                const float* ptr = gp + (long long)n_[h] * g.out_sstride + (long long)co * OHW + rem_[h];
-                cb[u] = ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int h = (wq + 4 * u) & 1;
+                const bool ok = pv[h] && bok[u];
+                cb[u] = ok ? __ldg(reinterpret_cast<const float4*>(gp + go[h] + boff[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             // ---- the stage must have been read by the MMAs of its previous use
             if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+                if (!gok[q]) continue;
                 const int rg = wq * 4 + q;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float4 v = ca[q][h];
-                    if (dxs[q] < 0) v = make_float4(ea[q][h], v.x, v.y, v.z);
-                    else if (dxs[q] > 0) v = make_float4(v.y, v.z, v.w, ea[q][h]);
+                    if (dxv[q] < 0) v = make_float4(ea[q][h], v.x, v.y, v.z);
+                    else if (dxv[q] > 0) v = make_float4(v.y, v.z, v.w, ea[q][h]);
                     float4 hi, lo;
                     split4(v, hi, lo);
                     const int o = rg * 256 + h * 128 + lane * 4;       // ((rg*8 + kgroup) * 32) + (row%8)*4, kgroup = h*4 + lane/8
@@ -226,11 +253,23 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
         const int m = mt * TC_M + r;
         if (total > 0 && m < Mrows) {
             const int t = m / g.Cin, ci = m - t * g.Cin;
-            float* __restrict__ wrow = a.out + (long long)ci * KHW + t;
+            if (!swapped) {
+                // row = (tap, input channel), column = output channel:  Wbar[co][ci][t]
+                float* __restrict__ wrow = a.out + (long long)ci * KHW + t;
 #pragma unroll
-            for (int i = 0; i < BN; ++i) {
-                const int co = nt * BN + i;
-                if (co < g.Cout) atomicAdd(wrow + (long long)co * g.Cin * KHW, acc[i]);
+                for (int i = 0; i < BN; ++i) {
+                    const int co = nt * BN + i;
+                    if (co < g.Cout) atomicAdd(wrow + (long long)co * g.Cin * KHW, acc[i]);
+                }
+            } else {
+                // operands were exchanged (launcher): row = (mirrored tap, OUTPUT channel), column = INPUT channel;
+                // g.Cin is the layer's Cout and g.Cout its Cin here
+                float* __restrict__ wrow = a.out + (long long)ci * g.Cout * KHW + (KHW - 1 - t);
+#pragma unroll
+                for (int i = 0; i < BN; ++i) {
+                    const int c2 = nt * BN + i;
+                    if (c2 < g.Cout) atomicAdd(wrow + (long long)c2 * KHW, acc[i]);
+                }
             }
         }
     } else {
@@ -282,7 +321,7 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
 }
 
 template <int BN>
-static int launch_wg_t(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntiles, int ksplit) {
+static int launch_wg_t(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntiles, int ksplit, int swapped) {
     constexpr size_t smem = WgSmem<BN>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
@@ -290,35 +329,47 @@ static int launch_wg_t(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntil
         if (e != cudaSuccess) { set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
         attr_set = true;
     }
-    conv_tc_wgrad_kernel<BN><<<mtiles * ntiles * ksplit, TC_THREADS, smem, st>>>(a, mtiles, ntiles, ksplit);
+    conv_tc_wgrad_kernel<BN><<<mtiles * ntiles * ksplit, TC_THREADS, smem, st>>>(a, mtiles, ntiles, ksplit, swapped);
     return 1;
 }
 
 // Returns 1 when the tensor-core kernel was launched, 0 when the layer is not eligible, <0 on error.
-int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a) {
+int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a0) {
     const int mode = get_tc_mode();
     if (mode == 0) return 0;
-    const ConvGeom& g = a.g;
+    ConvKArgs a = a0;
+    ConvGeom& g = a.g;
     const long long J = (long long)g.batch * g.OH * g.OW;
-    if (g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || (g.Cin & 7) || g.KW - 1 - g.pw > 1 || g.pw > 1) return 0;
+    if (g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || g.KW - 1 - g.pw > 1 || g.pw > 1) return 0;
     if (((uintptr_t)a.out & 3) != 0 || (g.in_sstride & 3) || (g.out_sstride & 3)) return 0;
     for (int p = 0; p < a.npairs; ++p)
         if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) return 0;
-    if (J >= (1LL << 31)) return 0;
+    if (J >= (1LL << 31) || (long long)g.Cin * g.H * g.W >= (1LL << 31) || (long long)g.Cout * g.OH * g.OW >= (1LL << 31)) return 0;
     if (mode == 1 && J < 1024) return 0;
+    // The shifted (per-tap) operand is replicated KH*KW times along the M dimension: shift the one with fewer
+    // channels.  For a "same" convolution the sum over output pixels of g[co,px] x[ci,px+s] equals the sum
+    // over input pixels of x[ci,px'] g[co,px'-s]: exchange the operands, mirror the taps.
+    int swapped = 0;
+    if (g.Cout < g.Cin && g.H == g.OH && g.W == g.OW && 2 * g.ph == g.KH - 1 && 2 * g.pw == g.KW - 1) {
+        swapped = 1;
+        for (int p = 0; p < a.npairs; ++p) std::swap(a.act[p], a.wt[p]);
+        std::swap(g.Cin, g.Cout);
+        std::swap(g.in_sstride, g.out_sstride);
+    }
     const int BN = tc_choose_bn(g.Cout);
     const int mtiles = (g.KH * g.KW * g.Cin + TC_M - 1) / TC_M;
     const int ntiles = (g.Cout + BN - 1) / BN;
     const int nkb = (int)((J + TC_KB - 1) / TC_KB);
     int ksplit = std::max(1, kNumSMs / (mtiles * ntiles));
-    ksplit = std::min(ksplit, nkb);
+    static const int min_kb = getenv("B2S_WG_MINKB") ? atoi(getenv("B2S_WG_MINKB")) : 8;
+    ksplit = std::min(ksplit, std::max(1, nkb / min_kb));      // at least min_kb k-blocks per CTA and pair
     switch (BN) {
-    case 16: return launch_wg_t<16>(st, a, mtiles, ntiles, ksplit);
-    case 32: return launch_wg_t<32>(st, a, mtiles, ntiles, ksplit);
-    case 48: return launch_wg_t<48>(st, a, mtiles, ntiles, ksplit);
-    case 64: return launch_wg_t<64>(st, a, mtiles, ntiles, ksplit);
-    case 96: return launch_wg_t<96>(st, a, mtiles, ntiles, ksplit);
-    default: return launch_wg_t<128>(st, a, mtiles, ntiles, ksplit);
+    case 16: return launch_wg_t<16>(st, a, mtiles, ntiles, ksplit, swapped);
+    case 32: return launch_wg_t<32>(st, a, mtiles, ntiles, ksplit, swapped);
+    case 48: return launch_wg_t<48>(st, a, mtiles, ntiles, ksplit, swapped);
+    case 64: return launch_wg_t<64>(st, a, mtiles, ntiles, ksplit, swapped);
+    case 96: return launch_wg_t<96>(st, a, mtiles, ntiles, ksplit, swapped);
+    default: return launch_wg_t<128>(st, a, mtiles, ntiles, ksplit, swapped);
     }
 }
 
