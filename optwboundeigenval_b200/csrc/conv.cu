@@ -535,6 +535,14 @@ static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
                              (double)g.Cout * g.Cin * g.KH * g.KW * a.npairs);
     ProfScope prof(MODE == MODE_FWD ? "conv_fwd" : "conv_dgrad", 2.0 * macs * a.npairs, io, st);
     {
+        const int rc = try_launch_conv_tma(MODE, st, a);     // TMA-fed tcgen05 path (stride 1, 16-byte row pitch)
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            B2S_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+    {
         const int rc = try_launch_conv_tc(MODE, st, a);      // tcgen05 path for wide layers
         if (rc < 0) return rc;
         if (rc == 1) {

@@ -41,6 +41,8 @@ int launch_tc_pack(cudaStream_t st, const TcPackJob* d_jobs, int njobs, long lon
 // mode: MODE_FWD or MODE_DGRAD.  Returns 1 when the kernel was launched, 0 when the layer is not
 // eligible (no packed image, too few pixels), <0 on error.
 int try_launch_conv_tc(int mode, cudaStream_t st, const ConvKArgs& a);
+// TMA-fed variant (conv_tma.cu): activation tiles land in swizzled shared memory as the MN-major operand.
+int try_launch_conv_tma(int mode, cudaStream_t st, const ConvKArgs& a);
 // weight-gradient contraction on the tensor cores (conv_tc_wgrad.cu): a.act = x jets, a.wt = adjoint jets,
 // a.out = the layer's slice of the flat gradient.  Same return convention.
 int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a);
