@@ -317,6 +317,7 @@ template <int K, int VEC> __global__ void __launch_bounds__(256) bn_bwd_apply_ke
 // happen between the phases.
 template <int K, int VEC>
 __global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnArgs a, int do_stats) {
+    pdl_trigger();
     if (do_stats) bn_fwd_stats_body<K, VEC>(a);
     __threadfence();
     cg::this_grid().sync();
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnArgs a, int d
 }
 template <int K, int VEC>
 __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float ps) {
+    pdl_trigger();
     bn_bwd_stats_body<K, VEC>(a);
     __threadfence();
     cg::this_grid().sync();
@@ -335,6 +337,8 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float
 // grid fits beside whatever the weight-gradient stream is running), the second read hits L1/L2.
 template <int K, int VEC>
 __global__ void __launch_bounds__(1024) bn_fwd_chan_kernel(const BnArgs a, int do_stats) {
+    pdl_trigger();
+    pdl_wait();
     if (do_stats) bn_fwd_stats_body<K, VEC>(a);
     __threadfence();
     __syncthreads();
@@ -342,6 +346,8 @@ __global__ void __launch_bounds__(1024) bn_fwd_chan_kernel(const BnArgs a, int d
 }
 template <int K, int VEC>
 __global__ void __launch_bounds__(1024) bn_bwd_chan_kernel(const BnArgs a, float ps) {
+    pdl_trigger();
+    pdl_wait();
     bn_bwd_stats_body<K, VEC>(a);
     __threadfence();
     __syncthreads();
@@ -416,7 +422,7 @@ int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stat
     ProfScope prof("bn_fwd_fused", 16.0 * elems, 4.0 * elems * (2 * order + 3), st);
     const int vec = bn_vec(a);
     if (const int blk = bn_chan_block(a, vec)) {
-#define CALL(K_, V_) bn_fwd_chan_kernel<K_, V_><<<dim3(a.C, 1), blk, 0, st>>>(a, do_stats)
+#define CALL(K_, V_) launch_pdl(bn_fwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, a, do_stats)
         B2S_BN_DISPATCH(order, vec, CALL);
 #undef CALL
         B2S_LAUNCH_CHECK();
@@ -433,7 +439,7 @@ int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     const int vec = bn_vec(a);
     if (const int blk = bn_chan_block(a, vec)) {
         const float ps = a.pgrad_scale;
-#define CALL(K_, V_) bn_bwd_chan_kernel<K_, V_><<<dim3(a.C, 1), blk, 0, st>>>(a, ps)
+#define CALL(K_, V_) launch_pdl(bn_bwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, a, ps)
         B2S_BN_DISPATCH(order, vec, CALL);
 #undef CALL
         B2S_LAUNCH_CHECK();

@@ -87,10 +87,58 @@ __device__ __forceinline__ void tm_stamp(long long* trace, int role, uint32_t kb
 #endif
 }
 
+// one pixel's BN output channels: out[c] (+)= acc[c] with the ReLU variant; channel stride cs, mrem valid channels.
+// Loads (previous value, ReLU reference) are issued eight channels ahead of the stores that need them.
+template <int BN, bool ACC, int RELU>
+__device__ __forceinline__ void tm_epilogue(const float (&acc)[BN], float* __restrict__ outp, const float* __restrict__ refp,
+                                            const int cs, const int mrem) {
+    if (mrem >= BN) {                             // full tile: no per-channel predicates at all
+#pragma unroll
+        for (int i0 = 0; i0 < BN; i0 += 8) {
+            float prev[8], ref[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (ACC) prev[i] = outp[(long long)(i0 + i) * cs];
+                if (RELU == 2) ref[i] = __ldg(refp + (long long)(i0 + i) * cs);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float val = acc[i0 + i];
+                if (ACC) val += prev[i];
+                if (RELU == 1) val = fmaxf(val, 0.f);
+                if (RELU == 2) val = ref[i] > 0.f ? val : 0.f;
+                outp[(long long)(i0 + i) * cs] = val;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i0 = 0; i0 < BN; i0 += 8) {
+            float prev[8], ref[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool okc = i0 + i < mrem;
+                if (ACC) prev[i] = okc ? outp[(long long)(i0 + i) * cs] : 0.f;
+                if (RELU == 2) ref[i] = okc ? __ldg(refp + (long long)(i0 + i) * cs) : 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i0 + i < mrem) {
+                    float val = acc[i0 + i];
+                    if (ACC) val += prev[i];
+                    if (RELU == 1) val = fmaxf(val, 0.f);
+                    if (RELU == 2) val = ref[i] > 0.f ? val : 0.f;
+                    outp[(long long)(i0 + i) * cs] = val;
+                }
+            }
+        }
+    }
+}
+
 template <int BN, int MODE, int PT>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const TmaTiling tg) {
     extern __shared__ __align__(1024) uint8_t tm_smem[];
+    pdl_trigger();                                            // the next kernel may be scheduled behind this one
     constexpr int B_TILE_FLOATS = BN * TC_KB;                 // one of hi / lo
     constexpr uint32_t B_STAGE_BYTES = 2u * B_TILE_FLOATS * sizeof(float);
     constexpr uint32_t RAW_BYTES = TM_RAW_FLOATS * sizeof(float);
@@ -148,6 +196,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                               // everything above overlapped the previous kernel's tail
 
     if (warp < 8) {
         // ===================== transform: landed box -> registers (shift, split) -> TMEM =====================
@@ -276,38 +325,30 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                     if (tid == 256) tm_stamp(a.trace, 2, grp, 2);
                 }
             }
-            // epilogue: lane = pixel, so every per-channel store is one coalesced 128-byte row.  Reads the
-            // epilogue depends on (previous adjoint, ReLU reference) are issued in batches of 8 ahead of
-            // the stores so that they overlap instead of forming a load -> store chain.
+            // epilogue: lane = pixel, so every per-channel store is one coalesced 128-byte row.  The variant
+            // (accumulate, ReLU mode) is chosen ONCE per tile: the generic form (flags tested per element) compiled
+            // to ~20 instructions and a branch per channel, executed by one warp per scheduler -- 6600 clocks per
+            // 48-channel tile in the timeline, more than the whole k-loop of a 1x1 convolution.
             const long long j = (long long)jt * TC_M + r;
             if (j < J) {
                 const int n = (int)(j / HWd);
                 const int pix = (int)(j - (long long)n * HWd);
                 const int m0 = nt * BN;
-                float* __restrict__ outp = a.out + (long long)n * d_ss + pix + (long long)m0 * HWd;
-                const float* __restrict__ refp = a.relu_mode == 2 ? a.relu_ref + (long long)n * d_ss + pix + (long long)m0 * HWd : nullptr;
-                const float* __restrict__ bias = a.bias;
+                const long long off = (long long)n * d_ss + pix + (long long)m0 * HWd;
                 const int mrem = Cd - m0;                 // valid channels of this tile
-                const bool need_out = a.accumulate != 0;
+                if (a.bias) {
 #pragma unroll
-                for (int i0 = 0; i0 < BN; i0 += 8) {
-                    float prev[8], ref[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool okc = i0 + i < mrem;
-                        prev[i] = (need_out && okc) ? outp[(long long)(i0 + i) * HWd] : 0.f;
-                        ref[i] = (refp && okc) ? __ldg(refp + (long long)(i0 + i) * HWd) : 1.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (i0 + i < mrem) {
-                            float val = acc[i0 + i] + prev[i];
-                            if (bias) val += __ldg(bias + m0 + i0 + i);
-                            if (a.relu_mode == 1) val = val > 0.f ? val : 0.f;
-                            else if (!(ref[i] > 0.f)) val = 0.f;
-                            outp[(long long)(i0 + i) * HWd] = val;
-                        }
-                    }
+                    for (int i = 0; i < BN; ++i)
+                        if (i < mrem) acc[i] += __ldg(a.bias + m0 + i);
+                }
+                const int variant = (a.accumulate != 0 ? 1 : 0) + 2 * a.relu_mode;
+                switch (variant) {
+                case 0: tm_epilogue<BN, false, 0>(acc, a.out + off, nullptr, HWd, mrem); break;
+                case 1: tm_epilogue<BN, true, 0>(acc, a.out + off, nullptr, HWd, mrem); break;
+                case 2: tm_epilogue<BN, false, 1>(acc, a.out + off, nullptr, HWd, mrem); break;
+                case 3: tm_epilogue<BN, true, 1>(acc, a.out + off, nullptr, HWd, mrem); break;
+                case 4: tm_epilogue<BN, false, 2>(acc, a.out + off, a.relu_ref + off, HWd, mrem); break;
+                default: tm_epilogue<BN, true, 2>(acc, a.out + off, a.relu_ref + off, HWd, mrem); break;
                 }
             }
         }
@@ -490,7 +531,10 @@ static int launch_tma_t(cudaStream_t st, const ConvKArgs& a, const TmaMaps& maps
         }
         return 1;
     }
-    conv_tma_kernel<BN, MODE, PT><<<grid, TM_THREADS, smem, st>>>(a, maps, tg);
+    {
+        const cudaError_t e = launch_pdl(conv_tma_kernel<BN, MODE, PT>, dim3(grid), dim3(TM_THREADS), smem, st, a, maps, tg);
+        if (e != cudaSuccess) { set_error("conv_tma launch: %s", cudaGetErrorString(e)); return -3; }
+    }
     if (tg.dbg) {
         const cudaError_t e = cudaStreamSynchronize(st);
         unsigned flag = 0;

@@ -35,6 +35,10 @@ thread_local long long g_launches = 0;
 static thread_local bool g_counting_paused = false;
 static thread_local long long g_capture_count = 0;
 
+bool pdl_enabled() {
+    static const bool on = getenv("B2S_PDL") && atoi(getenv("B2S_PDL")) != 0;   // measured: no gain inside captured graphs, off by default
+    return on;
+}
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
