@@ -420,6 +420,7 @@ static int launch_bwd_fused_t(cudaStream_t st, const BnArgs& a) {
 int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stats) {
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_fwd_fused", 16.0 * elems, 4.0 * elems * (2 * order + 3), st);
+    if (skip_family("bn_fwd")) return 0;
     const int vec = bn_vec(a);
     if (const int blk = bn_chan_block(a, vec)) {
 #define CALL(K_, V_) launch_pdl(bn_fwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, a, do_stats)
@@ -436,6 +437,7 @@ int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stat
 int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     const double elems = (double)a.batch * a.C * a.HW;
     ProfScope prof("bn_bwd_fused", 16.0 * elems, 4.0 * elems * (4 * order + 7), st);
+    if (skip_family("bn_bwd")) return 0;
     const int vec = bn_vec(a);
     if (const int blk = bn_chan_block(a, vec)) {
         const float ps = a.pgrad_scale;

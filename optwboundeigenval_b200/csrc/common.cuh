@@ -70,6 +70,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// timing experiments only (B2S_SKIP=conv_fwd,bn_bwd,...): the named kernel families are not launched, so
+// that the difference of two graph-replayed pass times is the in-situ cost of a family.  Results are garbage.
+bool skip_family(const char* name);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs

@@ -534,6 +534,7 @@ static int launch_gather(cudaStream_t st, const ConvKArgs& a) {
     const double io = 4.0 * ((double)g.batch * g.Cin * g.H * g.W * a.npairs + (double)g.batch * g.Cout * g.OH * g.OW +
                              (double)g.Cout * g.Cin * g.KH * g.KW * a.npairs);
     ProfScope prof(MODE == MODE_FWD ? "conv_fwd" : "conv_dgrad", 2.0 * macs * a.npairs, io, st);
+    if (skip_family(MODE == MODE_FWD ? "conv_fwd" : "conv_dgrad")) return 0;
     {
         const int rc = try_launch_conv_tma(MODE, st, a);     // TMA-fed tcgen05 path (stride 1, 16-byte row pitch)
         if (rc < 0) return rc;
@@ -600,6 +601,7 @@ int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const floa
     const double macs = (double)g.batch * g.OH * g.OW * g.Cout * g.Cin * g.KH * g.KW;
     ProfScope prof("conv_wgrad", 2.0 * macs * npairs,
                    4.0 * npairs * ((double)g.batch * g.Cin * g.H * g.W + (double)g.batch * g.Cout * g.OH * g.OW), st);
+    if (skip_family("conv_wgrad")) return 0;
     {
         const int rc = try_launch_wgrad_tc(st, a);           // tcgen05 path
         if (rc < 0) return rc;

@@ -27,6 +27,9 @@
 namespace b2s {
 
 constexpr int WG_NST = 3;                      // shared-memory stages
+constexpr int WG_G = 4;                        // k-blocks accumulated in TMEM between drains (as conv_tma.cu: 16 truncating
+                                               // accumulations of K = 8 instead of 4; the drain was ~3 NACC BN TMEM columns
+                                               // per thread and k-block)
 constexpr int WG_A_FLOATS = TC_M * TC_KB;      // one of hi / lo
 
 template <int BN>
@@ -226,29 +229,32 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
         float acc[BN];
 #pragma unroll
         for (int i = 0; i < BN; ++i) acc[i] = 0.f;
-        for (int i = 0; i < total; ++i) {
-            const float sc = a.scale[i / nloc];
-            const int b = i & 1;
-            mbar_wait(&d_full[b], (i >> 1) & 1);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t d0 = lane_addr + TC_DCOL0 + b * TC_DCOLS;
+        uint32_t grp = 0;
+        for (int p = 0; p < a.npairs; ++p) {
+            const float sc = a.scale[p];
+            for (int k0 = 0; k0 < nloc; k0 += WG_G, ++grp) {
+                const int b = grp & 1;
+                mbar_wait(&d_full[b], (grp >> 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+                const uint32_t d0 = lane_addr + TC_DCOL0 + b * TC_DCOLS;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[NACC][16];
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[NACC][16];
 #pragma unroll
-                for (int q2 = 0; q2 < NACC; ++q2) tmem_ld16(d0 + q2 * BN + c0, v[q2]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    for (int q2 = 0; q2 < NACC; ++q2) tmem_ld16(d0 + q2 * BN + c0, v[q2]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float d = __uint_as_float(v[0][e]);
-                    if (NACC >= 2) d += __uint_as_float(v[1][e]);
-                    if (NACC >= 3) d += __uint_as_float(v[2][e]);
-                    acc[c0 + e] = fmaf(d, sc, acc[c0 + e]);
+                    for (int e = 0; e < 16; ++e) {
+                        float d = __uint_as_float(v[0][e]);
+                        if (NACC >= 2) d += __uint_as_float(v[1][e]);
+                        if (NACC >= 3) d += __uint_as_float(v[2][e]);
+                        acc[c0 + e] = fmaf(d, sc, acc[c0 + e]);
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(&d_empty[b]);
             }
-            tc_fence_before();
-            mbar_arrive(&d_empty[b]);
         }
         const int m = mt * TC_M + r;
         if (total > 0 && m < Mrows) {
@@ -282,32 +288,38 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
             constexpr int NACC = tc_nacc(BN) > 3 ? 3 : tc_nacc(BN);
             constexpr uint32_t STAGE16 = (uint32_t)(S::STAGE_FLOATS * 4) >> 4;
             constexpr uint32_t A16 = (uint32_t)(WG_A_FLOATS * 4) >> 4, B16 = (uint32_t)(S::B_FLOATS * 4) >> 4;
+            uint32_t grp = 0;
             for (int i = 0; i < total; ++i) {
                 const int s = i % WG_NST;
                 const uint32_t round = i / WG_NST;
-                const int b = i & 1;
-                const uint32_t use = i >> 1;
+                const int kk = i % nloc;                              // k-block inside its pair: drain groups never span pairs
+                const bool first = (kk % WG_G) == 0;
+                const bool last = (kk % WG_G) == WG_G - 1 || kk == nloc - 1;
+                const int b = grp & 1;
+                const uint32_t use = grp >> 1;
                 mbar_wait(&ab_full[s], round & 1);
-                if (use > 0) mbar_wait(&d_empty[b], (use - 1) & 1);
+                if (first && use > 0) mbar_wait(&d_empty[b], (use - 1) & 1);
                 __syncwarp();
                 tc_fence_after();
                 const uint32_t d_addr = tmem_u + TC_DCOL0 + b * TC_DCOLS;
                 const uint64_t dAh = desc0 + (uint64_t)(s * STAGE16), dAl = dAh + A16;
                 const uint64_t dBh = dAl + A16, dBl = dBh + B16;
+                const uint32_t cont = first ? 0u : 1u;                // accumulate onto the group's earlier k-blocks
                 if (elect_one()) {
                     auto acc_of = [](int term) { return NACC == 3 ? term : NACC == 2 ? (term == 2 ? 1 : 0) : 0; };
 #pragma unroll
                     for (int ks = 0; ks < TC_KB / 8; ++ks) {
                         const uint64_t ko = (uint64_t)(ks * 16);
-                        const uint32_t fresh = ks >= 1;
-                        umma_tf32_ss(d_addr + acc_of(0) * BN, dAh + ko, dBl + ko, idesc, fresh);
-                        umma_tf32_ss(d_addr + acc_of(1) * BN, dAl + ko, dBh + ko, idesc, NACC <= 2 ? 1u : fresh);
-                        umma_tf32_ss(d_addr + acc_of(2) * BN, dAh + ko, dBh + ko, idesc, NACC == 1 ? 1u : fresh);
+                        const uint32_t accf = ks >= 1 ? 1u : cont;
+                        umma_tf32_ss(d_addr + acc_of(0) * BN, dAh + ko, dBl + ko, idesc, accf);
+                        umma_tf32_ss(d_addr + acc_of(1) * BN, dAl + ko, dBh + ko, idesc, NACC <= 2 ? 1u : accf);
+                        umma_tf32_ss(d_addr + acc_of(2) * BN, dAh + ko, dBh + ko, idesc, NACC == 1 ? 1u : accf);
                     }
                     umma_commit(&ab_free[s]);
-                    umma_commit(&d_full[b]);
+                    if (last) umma_commit(&d_full[b]);
                 }
                 __syncwarp();
+                if (last) ++grp;
             }
         }
     }

@@ -35,6 +35,14 @@ thread_local long long g_launches = 0;
 static thread_local bool g_counting_paused = false;
 static thread_local long long g_capture_count = 0;
 
+bool skip_family(const char* name) {
+    static const char* list = getenv("B2S_SKIP");
+    if (!list) return false;
+    const char* hit = strstr(list, name);
+    if (!hit) return false;
+    const char end = hit[strlen(name)];
+    return (hit == list || hit[-1] == ',') && (end == 0 || end == ',');
+}
 bool pdl_enabled() {
     static const bool on = getenv("B2S_PDL") && atoi(getenv("B2S_PDL")) != 0;   // measured: no gain inside captured graphs, off by default
     return on;
@@ -104,8 +112,14 @@ struct b2s_plan {
     int device = 0;
     cudaStream_t caller = nullptr;    // stream the caller's tensors are ordered on
     cudaStream_t stream = nullptr;    // plan-owned work stream (graphs cannot be captured on stream 0)
-    cudaStream_t side = nullptr;      // weight-gradient contractions run here, off the adjoint critical path
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    static constexpr int kMaxSide = 8;
+    cudaStream_t sides[kMaxSide] = {};   // weight-gradient contractions run here (round robin), off the adjoint critical path
+    cudaEvent_t ev_joins[kMaxSide] = {};
+    int n_side = 4;                   // B2S_SIDE_STREAMS: independent weight-gradient kernels of different layers overlap
+    int side_next = 0;
+    unsigned side_mask = 0;           // side streams with work in flight in this pass
+    cudaStream_t side = nullptr;      // the side stream chosen by the last fork_side()
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_fork = nullptr;
     bool side_used = false;
     bool use_graphs = true;
     std::vector<b2s_tensor> tensors;
@@ -356,15 +370,24 @@ static int forward(b2s_plan* p, int K) {
 // the main stream) so the adjoint chain  dgrad -> BN backward -> dgrad ...  does not wait for it.
 static int fork_side(b2s_plan* p) {
     if (!p->wgrad_side) return 0;
+    const int i = p->side_next;
+    p->side_next = (i + 1) % p->n_side;
+    p->side = p->sides[i];
     B2S_CUDA(cudaEventRecord(p->ev_fork, p->stream));
     B2S_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    p->side_mask |= 1u << i;
     p->side_used = true;
     return 0;
 }
 static int join_side(b2s_plan* p) {
     if (!p->side_used) return 0;
-    B2S_CUDA(cudaEventRecord(p->ev_join, p->side));
-    B2S_CUDA(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+    for (int i = 0; i < p->n_side; ++i) {
+        if (!(p->side_mask & (1u << i))) continue;
+        B2S_CUDA(cudaEventRecord(p->ev_joins[i], p->sides[i]));
+        B2S_CUDA(cudaStreamWaitEvent(p->stream, p->ev_joins[i], 0));
+    }
+    p->side_mask = 0;
+    p->side_next = 0;
     p->side_used = false;
     return 0;
 }
@@ -730,14 +753,21 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     int rc = 0;
     auto fail = [&](int code) { b2s_plan_destroy(p); return code; };
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess) {
         set_error("b2s_plan_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(-2);
     }
+    if (const char* e = getenv("B2S_SIDE_STREAMS")) p->n_side = std::max(1, std::min((int)b2s_plan::kMaxSide, atoi(e)));
+    for (int i = 0; i < p->n_side; ++i) {
+        if (cudaStreamCreateWithFlags(&p->sides[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_joins[i], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("b2s_plan_create: side stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(-2);
+        }
+    }
+    p->side = p->sides[0];
     if ((rc = alloc_order(p, 0)) != 0) return fail(rc);
     if ((rc = alloc_order(p, 1)) != 0) return fail(rc);
     const b2s_tensor& L = tensors[logits];
@@ -828,9 +858,11 @@ int b2s_plan_destroy(b2s_plan* p) {
     cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
     if (p->pi) b2s_pi_destroy(p->pi);
     if (p->comm) comm_destroy(p->comm);
-    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
+    for (int i = 0; i < b2s_plan::kMaxSide; ++i) {
+        if (p->sides[i]) { cudaStreamSynchronize(p->sides[i]); cudaStreamDestroy(p->sides[i]); }
+        if (p->ev_joins[i]) cudaEventDestroy(p->ev_joins[i]);
+    }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->ev_out) cudaEventDestroy(p->ev_out);
     if (p->stream) cudaStreamDestroy(p->stream);

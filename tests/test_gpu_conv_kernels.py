@@ -1,0 +1,35 @@
+"""Kernel-level parity of the tensor-core contractions (conv_tma.cu, conv_tc.cu, conv_tc_wgrad.cu), through the
+C ABI: a 1x1 convolution feeding a kxk convolution; the forward output, the input adjoint (dgrad) and the weight
+gradient (wgrad) of the second convolution are compared with an fp64 torch evaluation of the same fp32 inputs.
+
+The shapes are the three DenseNet3 block geometries (32x32, 16x16, 8x8 images; the 8x8 tile holds two images),
+ragged channel counts (chunk tails, 1 k-step k-blocks) and both kernel sizes.  Tolerance: fp32-accurate,
+1e-5 relative L2 (3xTF32 measured 2e-7 .. 4e-7), i.e. 10x inside the 1e-4 budget of BASELINE.json.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("W,cin,cout,batch,k", [
+    (32, 48, 12, 4, 3),      # DenseNet3 block 1 bottleneck 3x3 (two channel chunks: 32 + 16)
+    (32, 60, 48, 4, 1),      # ... and its 1x1 (ragged chunk tail, BN = 48)
+    (16, 40, 12, 8, 3),      # block 2; 40 channels: the tail chunk is a single k-step
+    (8, 132, 48, 32, 1),     # block 3: tile = two 8x8 images, five chunks
+    (8, 48, 12, 32, 3),
+    (32, 12, 24, 3, 3),      # batch 3: ragged last pixel tile
+])
+def test_tensor_core_contractions_match_fp64(W, cin, cout, batch, k):
+    import tma_probe
+    errs = tma_probe.probe(W, cin, cout, batch, k, verbose=False)
+    for (mode, what), e in errs.items():
+        assert e < 1e-5, "mode %d %s: relative L2 error %.3e" % (mode, what, e)
+    # the tensor-core path must not be (much) less accurate than the fp32 CUDA-core path
+    for what in ("fwd", "dgrad", "wgrad"):
+        assert errs[(2, what)] < 4 * errs[(0, what)] + 5e-7, (what, errs)

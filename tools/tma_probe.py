@@ -36,13 +36,10 @@ def read_tensor(plan, adjoint, order, t, batch):
     return out
 
 
-def main():
-    W = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-    cin = int(sys.argv[2]) if len(sys.argv) > 2 else 48
-    cout = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-    batch = int(sys.argv[4]) if len(sys.argv) > 4 else 4
-    k = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+def probe(W=32, cin=48, cout=12, batch=4, k=3, verbose=True):
+    """returns {(mode, what): relative L2 error against fp64} for what in fwd / dgrad / wgrad, mode in 0 (CUDA cores) / 2 (tensor cores)"""
     lib = _lib.load()
+    errs = {}
     torch.manual_seed(3)
     m = TwoConv(cin, cout, k).train()
     x = torch.randn(batch, 16, W, W)
@@ -56,22 +53,27 @@ def main():
     nn.CrossEntropyLoss()(out, y).backward()
     want_f = h2.detach().numpy()
     want_b = h1.grad.numpy()
+    want_w = md.c2.weight.grad.numpy()
+    w_off = md.c1.weight.numel()
     for mode in (0, 2):
         clear_plans()
         _lib.check(lib.b2s_set_tensor_core_mode(mode))
         op = B200HVPOperator(m, [x, y], nn.CrossEntropyLoss())
-        op.prepare_grad()
+        grad = op.prepare_grad()
         torch.cuda.synchronize()
         plan = op.plan
         convs = [o for o in plan.tape.ops if o.kind == 1]
         got_f = read_tensor(plan, 0, 0, convs[1].out, batch).astype(np.float64)
         got_b = read_tensor(plan, 1, 0, convs[0].out, batch).astype(np.float64)
-        for name, got, want in (("fwd", got_f, want_f), ("dgrad", got_b, want_b)):
+        got_w = grad.cpu().numpy()[w_off:w_off + want_w.size].reshape(want_w.shape)
+        for name, got, want in (("fwd", got_f, want_f), ("dgrad", got_b, want_b), ("wgrad", got_w, want_w)):
             d = got - want
-            print("W=%d Cin=%d Cout=%d k=%d batch=%d mode=%d %-5s rel_l2 %.3e  max_rel %.3e" % (
+            errs[(mode, name)] = float(np.linalg.norm(d) / np.linalg.norm(want))
+            if verbose:
+              print("W=%d Cin=%d Cout=%d k=%d batch=%d mode=%d %-5s rel_l2 %.3e  max_rel %.3e" % (
                 W, cin, cout, k, batch, mode, name, np.linalg.norm(d) / np.linalg.norm(want),
                 float(np.abs(d).max() / np.abs(want).mean())), flush=True)
-            if mode == 2 and np.linalg.norm(d) / np.linalg.norm(want) > 1e-4:
+            if verbose and name != "wgrad" and mode == 2 and np.linalg.norm(d) / np.linalg.norm(want) > 1e-4:
                 # where is it wrong?  per output channel / per pixel-row error
                 e = np.abs(d)
                 print("   err by channel:", np.round(e.mean(axis=(0, 2, 3)) / np.abs(want).mean(), 4)[:16])
@@ -80,7 +82,9 @@ def main():
                 print("   err by image  :", np.round(e.mean(axis=(1, 2, 3)) / np.abs(want).mean(), 4)[:8])
     _lib.check(lib.b2s_set_tensor_core_mode(1))
     clear_plans()
+    return errs
 
 
 if __name__ == "__main__":
-    main()
+    a = [int(v) for v in sys.argv[1:]]
+    probe(*a)
