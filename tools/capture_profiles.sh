@@ -13,9 +13,9 @@ T="python tools/ncu_target.py cifar_densenet 32 2"
 $T > gpurun_out/${R}_target_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:conv_tma_kernel -s 158 -c 4 -o gpurun_out/${R}_conv_tma -f $T > gpurun_out/${R}_ncu_conv_tma.log 2>&1
 echo "conv_tma rc $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_wgrad_kernel -s 80 -c 3 -o gpurun_out/${R}_conv_wgrad -f $T > gpurun_out/${R}_ncu_wgrad.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_wgrad_kernel -s 80 -c 2 -o gpurun_out/${R}_conv_wgrad -f $T > gpurun_out/${R}_ncu_wgrad.log 2>&1
 echo "wgrad rc $?"
-ncu --set full --clock-control none -k regex:bn_ -s 160 -c 4 -o gpurun_out/${R}_bn -f $T > gpurun_out/${R}_ncu_bn.log 2>&1
+ncu --set full --clock-control none -k regex:bn_ -s 160 -c 2 -o gpurun_out/${R}_bn -f $T > gpurun_out/${R}_ncu_bn.log 2>&1
 echo "bn rc $?"
 V="python tools/bench_vec.py"
 $V > gpurun_out/${R}_vec_plain.log 2>&1 &&
