@@ -39,11 +39,14 @@ struct WgSmem {
     static constexpr size_t BYTES = (size_t)WG_NST * STAGE_FLOATS * sizeof(float) + 256;
 };
 
+// hi = TF32 round-to-nearest (integer add of half an ulp, low 13 bits cleared: 2 instructions instead of the 4 of
+// cvt.rna's NaN-safe expansion), lo = v - hi exact in fp32; the tensor core reads the upper 19 bits of lo
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-    hi.x = __uint_as_float(to_tf32_bits(v.x)); lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & 0xffffe000u);
-    hi.y = __uint_as_float(to_tf32_bits(v.y)); lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & 0xffffe000u);
-    hi.z = __uint_as_float(to_tf32_bits(v.z)); lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & 0xffffe000u);
-    hi.w = __uint_as_float(to_tf32_bits(v.w)); lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & 0xffffe000u);
+    hi.x = tf32_hi(v.x); lo.x = v.x - hi.x;
+    hi.y = tf32_hi(v.y); lo.y = v.y - hi.y;
+    hi.z = tf32_hi(v.z); lo.z = v.z - hi.z;
+    hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
 }
 
 template <int BN>

@@ -96,21 +96,28 @@ def main():
     os.makedirs(DST, exist_ok=True)
     agg = launch_list()
     conv = summarize_rep("conv_tma")
-    summarize_rep("conv_wgrad")
+    wg = summarize_rep("conv_wgrad")
     summarize_rep("bn")
     vec = summarize_rep("vec")
-    if conv:
+    def per_launch(rows):
         per = []
-        for r in conv:
+        for r in rows:
             rd = to_bytes(*r["dram__bytes_read.sum"])
             wr = to_bytes(*r["dram__bytes_write.sum"])
             per.append({"kernel": r["Kernel Name"][0][:80], "grid": r["Grid Size"][0], "us": float(r["gpu__time_duration.sum"][0]),
                         "dram_bytes": rd + wr,
                         "tensor_pipe_active_pct": float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
                         "issue_active_pct": float(r["smsp__issue_active.avg.pct_of_peak_sustained_active"][0])})
-        js = {"kernel": "conv_tma_kernel (fwd + dgrad instances)", "capture": "%s_conv_tma.ncu-rep: ncu --set full, %d consecutive launches of "
-              "the Hv pass (DenseNet3 block 1, batch 32)" % (R, len(per)),
-              "dram_bytes_per_launch": sum(p["dram_bytes"] for p in per) / len(per), "launches": per}
+        return per
+
+    js = {}
+    for key, rows, what in (("conv_tma_kernel (fwd + dgrad instances)", conv, "conv_tma"), ("conv_wgrad", wg, "conv_wgrad")):
+        if rows:
+            per = per_launch(rows)
+            js[key] = {"capture": "%s_%s.ncu-rep: ncu --set full --clock-control none, %d consecutive launches of the Hv pass "
+                                  "(DenseNet3, batch 32, eager launches)" % (R, what, len(per)),
+                       "dram_bytes_per_launch": sum(p["dram_bytes"] for p in per) / len(per), "launches": per}
+    if js:
         with open(os.path.join(DST, "%s_ncu_top_kernel.json" % R), "w") as fh:
             json.dump(js, fh, indent=1)
     if vec:
