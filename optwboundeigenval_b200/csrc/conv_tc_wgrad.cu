@@ -249,9 +249,10 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        float d = __uint_as_float(v[0][e]);
-                        if (NACC >= 2) d += __uint_as_float(v[1][e]);
-                        if (NACC >= 3) d += __uint_as_float(v[2][e]);
+                        float d;
+                        if (NACC >= 3) d = (__uint_as_float(v[0][e]) + __uint_as_float(v[2][e])) + __uint_as_float(v[1][e]);
+                        else if (NACC == 2) d = __uint_as_float(v[1][e]) + __uint_as_float(v[0][e]);
+                        else d = __uint_as_float(v[0][e]);
                         acc[c0 + e] = fmaf(d, sc, acc[c0 + e]);
                     }
                 }
@@ -286,6 +287,7 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
         if (warp == TC_WARP_MMA) {
             // ===================== MMA issuer ======================================================
             const uint32_t idesc = umma_idesc_tf32(TC_M, BN);
+            const uint32_t idesc2 = umma_idesc_tf32(TC_M, 2 * BN <= 256 ? 2 * BN : BN);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
             const uint64_t desc0 = umma_desc(smem_u32(wg_smem), 128, 1024);      // stage 0, A hi, k-step 0
             constexpr int NACC = tc_nacc(BN) > 3 ? 3 : tc_nacc(BN);
@@ -309,14 +311,23 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
                 const uint64_t dBh = dAl + A16, dBl = dBh + B16;
                 const uint32_t cont = first ? 0u : 1u;                // accumulate onto the group's earlier k-blocks
                 if (elect_one()) {
-                    auto acc_of = [](int term) { return NACC == 3 ? term : NACC == 2 ? (term == 2 ? 1 : 0) : 0; };
+                    // set layout [lo*hi | hi*hi | hi*lo] (3 accumulators) or [hi*hi | hi*lo + lo*hi] (2): the hi and lo tiles of
+                    // B are adjacent in shared memory, so A_hi x [B_hi | B_lo] is one MMA with N = 2 BN (see conv_tma.cu)
 #pragma unroll
                     for (int ks = 0; ks < TC_KB / 8; ++ks) {
                         const uint64_t ko = (uint64_t)(ks * 16);
                         const uint32_t accf = ks >= 1 ? 1u : cont;
-                        umma_tf32_ss(d_addr + acc_of(0) * BN, dAh + ko, dBl + ko, idesc, accf);
-                        umma_tf32_ss(d_addr + acc_of(1) * BN, dAl + ko, dBh + ko, idesc, NACC <= 2 ? 1u : accf);
-                        umma_tf32_ss(d_addr + acc_of(2) * BN, dAh + ko, dBh + ko, idesc, NACC == 1 ? 1u : accf);
+                        if (NACC == 3) {
+                            umma_tf32_ss(d_addr + BN, dAh + ko, dBh + ko, idesc2, accf);
+                            umma_tf32_ss(d_addr, dAl + ko, dBh + ko, idesc, accf);
+                        } else if (NACC == 2) {
+                            umma_tf32_ss(d_addr, dAh + ko, dBh + ko, idesc2, accf);
+                            umma_tf32_ss(d_addr + BN, dAl + ko, dBh + ko, idesc, 1u);
+                        } else {
+                            umma_tf32_ss(d_addr, dAh + ko, dBl + ko, idesc, accf);
+                            umma_tf32_ss(d_addr, dAl + ko, dBh + ko, idesc, 1u);
+                            umma_tf32_ss(d_addr, dAh + ko, dBh + ko, idesc, 1u);
+                        }
                     }
                     umma_commit(&ab_free[s]);
                     if (last) umma_commit(&d_full[b]);

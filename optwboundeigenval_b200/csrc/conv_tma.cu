@@ -305,9 +305,11 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            float d = __uint_as_float(v[0][i]);
-                            if (NACC >= 2) d += __uint_as_float(v[1][i]);
-                            if (NACC >= 3) d += __uint_as_float(v[2][i]);
+                            // set layout [lo*hi | hi*hi | hi*lo] (3+ accumulators) or [hi*hi | hi*lo + lo*hi] (2): small terms first
+                            float d;
+                            if (NACC >= 3) d = (__uint_as_float(v[0][i]) + __uint_as_float(v[2][i])) + __uint_as_float(v[1][i]);
+                            else if (NACC == 2) d = __uint_as_float(v[1][i]) + __uint_as_float(v[0][i]);
+                            else d = __uint_as_float(v[0][i]);
                             acc[c0 + i] = fmaf(d, sc, acc[c0 + i]);
                         }
                         if (NACC == 6 && odd_set) {
@@ -317,7 +319,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                acc[c0 + i] = fmaf(__uint_as_float(w[0][i]) + __uint_as_float(w[1][i]) + __uint_as_float(w[2][i]), sc, acc[c0 + i]);
+                                acc[c0 + i] = fmaf((__uint_as_float(w[0][i]) + __uint_as_float(w[2][i])) + __uint_as_float(w[1][i]), sc, acc[c0 + i]);
                         }
                     }
                     tc_fence_before();
@@ -357,6 +359,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
         if (warp == TM_WARP_MMA) {
             // ===================== MMA issuer ======================================================
             const uint32_t idesc = umma_idesc_tf32(TC_M, BN);
+            const uint32_t idesc2 = umma_idesc_tf32(TC_M, 2 * BN <= 256 ? 2 * BN : BN);   // hi and lo weight tiles in one MMA
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);           // provably warp-uniform
             const uint64_t desc0 = umma_desc(smem_u32(bbuf), 128, 1024);         // stage 0, hi tile, k-step 0
             constexpr int NACC = tc_nacc(BN);
@@ -388,19 +391,29 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                                 const uint64_t dBl = dBh + (uint64_t)((B_TILE_FLOATS * 4) >> 4);
                                 const uint32_t ew = even_w ? 1u : 0u, ow = odd_w ? 1u : 0u;
                                 if (elect_one()) {
-                                    // accumulator of (term, k-step): terms 0 = hi*lo, 1 = lo*hi (small, added first), 2 = hi*hi
-                                    auto acc_of = [](int term, int ks) {
-                                        return NACC == 6 ? term + 3 * (ks & 1) : NACC == 3 ? term : NACC == 2 ? (term == 2 ? 1 : 0) : 0;
-                                    };
+                                    // Accumulator set of a k-step: with 6 accumulators odd and even k-steps use different sets
+                                    // (consecutive MMAs into one accumulator serialise on its read-modify-write latency).
+                                    // Layout of a set: [lo*hi | hi*hi | hi*lo], BN columns each.  The hi and lo weight tiles
+                                    // are adjacent in shared memory, so  A_hi x [B_hi | B_lo]  is ONE MMA with N = 2 BN:
+                                    // two instead of three MMAs per k-step (the issuing thread is the limiter of this kernel).
 #pragma unroll
                                     for (int ks = 0; ks < TC_KB / 8; ++ks) {
                                         if (ks < ksteps) {
                                             const uint64_t ko = (uint64_t)(ks * 16);      // 2 core matrices of 128 B per k-step
                                             // accumulate onto what this drain group has already put into the accumulator
                                             const uint32_t accf = NACC == 6 ? ((ks & 1) ? (ks >= 2 ? 1u : ow) : (ks >= 2 ? 1u : ew)) : (ks >= 1 ? 1u : ew);
-                                            umma_tf32_ts(d_addr + acc_of(0, ks) * BN, a_hi + ks * 8, dBl + ko, idesc, accf);
-                                            umma_tf32_ts(d_addr + acc_of(1, ks) * BN, a_lo + ks * 8, dBh + ko, idesc, NACC <= 2 ? 1u : accf);
-                                            umma_tf32_ts(d_addr + acc_of(2, ks) * BN, a_hi + ks * 8, dBh + ko, idesc, NACC == 1 ? 1u : accf);
+                                            if (NACC >= 3) {
+                                                const uint32_t set = d_addr + (NACC == 6 ? 3 * (ks & 1) * BN : 0);
+                                                umma_tf32_ts(set + BN, a_hi + ks * 8, dBh + ko, idesc2, accf);     // [hi*hi | hi*lo]
+                                                umma_tf32_ts(set, a_lo + ks * 8, dBh + ko, idesc, accf);           // lo*hi
+                                            } else if (NACC == 2) {
+                                                umma_tf32_ts(d_addr, a_hi + ks * 8, dBh + ko, idesc2, accf);       // [hi*hi | hi*lo]
+                                                umma_tf32_ts(d_addr + BN, a_lo + ks * 8, dBh + ko, idesc, 1u);     // hi*lo += lo*hi
+                                            } else {
+                                                umma_tf32_ts(d_addr, a_hi + ks * 8, dBl + ko, idesc, accf);
+                                                umma_tf32_ts(d_addr, a_lo + ks * 8, dBh + ko, idesc, 1u);
+                                                umma_tf32_ts(d_addr, a_hi + ks * 8, dBh + ko, idesc, 1u);
+                                            }
                                         }
                                     }
                                     umma_commit(&ab_free[s]);                 // arrives when these MMAs have read the stage
