@@ -185,7 +185,8 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     kind = args.config
     batch = args.batch or zoo.CONFIGS[kind][3]
     model, loss = zoo.build(kind)            # same seed on every rank: replicated parameters
@@ -251,7 +252,8 @@ def run_b200(args):
     # ---- roofline of the dominant kernel of the HVP pass (CUDA events around every launch, on the plan's stream) ----
     # conv_fwd and conv_dgrad are template instances of ONE kernel (conv_tma_kernel): they are one row here.
     peaks = _peaks()
-    prof = op.plan.profile(1, reps=3) if rank == 0 else []
+    # every rank runs the profiled pass (it contains the pass's NCCL all-reduces); rank 0 reports
+    prof = op.plan.profile(1, reps=3)
     line = None
     if rank == 0:
         fam = {}

@@ -224,6 +224,13 @@ int b2s_kfac_apply(b2s_plan* p, const double* d_r, double* d_out);
 int b2s_comm_unique_id(void* h_id128);                       /* 128 bytes, rank 0 */
 int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world);
 int b2s_comm_destroy(b2s_plan* p);
+/* One-shot all-reduce of the small per-layer BatchNorm sums over NVLink peer memory instead of NCCL (the reference
+ * has no counterpart: it is single-device).  After b2s_comm_init every rank calls
+ * b2s_comm_peer_local (allocates its exchange buffer, returns the 64-byte cudaIpcMemHandle), the handles are
+ * all-gathered by the host side, and b2s_comm_peer_attach maps the peers' buffers.  Optional: without it
+ * (or when peer access is unavailable) every all-reduce stays on NCCL. */
+int b2s_comm_peer_local(b2s_plan* p, void* h_handle64);
+int b2s_comm_peer_attach(b2s_plan* p, const void* h_handles /* world x 64 bytes, rank order */);
 
 #ifdef __cplusplus
 }

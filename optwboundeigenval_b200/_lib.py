@@ -70,6 +70,8 @@ SIGNATURES = {
     "b2s_comm_unique_id": (c_int32, [c_void_p]),
     "b2s_comm_init": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
     "b2s_comm_destroy": (c_int32, [c_void_p]),
+    "b2s_comm_peer_local": (c_int32, [c_void_p, c_void_p]),
+    "b2s_comm_peer_attach": (c_int32, [c_void_p, c_void_p]),
 }
 
 _lib = None

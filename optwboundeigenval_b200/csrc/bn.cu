@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "peer.cuh"
 
 namespace b2s {
 
@@ -321,6 +322,11 @@ __global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnArgs a, int d
     if (do_stats) bn_fwd_stats_body<K, VEC>(a);
     __threadfence();
     cg::this_grid().sync();
+    if (a.peer && do_stats) {          // data parallel: sum the per-channel sums over the GPUs, inside this kernel
+        if (blockIdx.x == 0 && blockIdx.y == 0) peer_exchange_block(a.fsum[K], 2 * a.C, *a.peer);
+        __threadfence();
+        cg::this_grid().sync();
+    }
     bn_fwd_apply_body<K, VEC>(a);
 }
 template <int K, int VEC>
@@ -329,6 +335,11 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float
     bn_bwd_stats_body<K, VEC>(a);
     __threadfence();
     cg::this_grid().sync();
+    if (a.peer) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) peer_exchange_block(a.bsum[K], 2 * a.C, *a.peer);
+        __threadfence();
+        cg::this_grid().sync();
+    }
     bn_bwd_apply_body<K, VEC>(a, ps);
 }
 
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_chan_kernel(const BnArgs a, float
 static inline int bn_chan_block(const BnArgs& a, int vec) {
     const long long per_chan = (long long)a.batch * a.HW / vec;      // chunks per channel
     static const long long limit = getenv("B2S_BN_CHAN_MAX") ? atoll(getenv("B2S_BN_CHAN_MAX")) : 1024;
-    if (a.C < 16 || per_chan > limit) return 0;
+    if (a.C < 16 || per_chan > limit || a.peer) return 0;       // the in-kernel exchange lives in the cooperative form
     return per_chan >= 4096 ? 1024 : per_chan >= 1024 ? 512 : 256;
 }
 

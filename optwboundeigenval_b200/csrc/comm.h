@@ -14,4 +14,14 @@ int comm_init(Comm** out, const void* h_id128, int rank, int world);
 int comm_destroy(Comm* c);
 int comm_allreduce_f32(Comm* c, float* buf, long long n, cudaStream_t st);
 int comm_allreduce_f64(Comm* c, double* buf, long long n, cudaStream_t st);
+// One-shot all-reduce of small fp64 vectors over NVLink peer memory (the per-layer BatchNorm sums: 2C doubles,
+// latency-bound): every rank publishes its vector in an exchange buffer that the peers have mapped
+// (cudaIpc), raises a sequence flag, polls the peers' flags and sums the peers' vectors in rank order with
+// direct loads through NVSwitch -- one small kernel, no ring, no proxy thread.  comm_allreduce_f64 uses it
+// for n <= the exchange capacity once the peers are attached, NCCL otherwise.
+int comm_peer_local(Comm* c, void* h_handle64);                 // allocate the exchange buffer, return its IPC handle
+int comm_peer_attach(Comm* c, const void* h_handles);           // world x 64 bytes, rank order
+struct PeerCtx;
+// device-resident exchange context for kernels that do the exchange themselves (peer.cuh), NULL when unavailable
+const PeerCtx* comm_peer_ctx(Comm* c);
 }  // namespace b2s

@@ -1,0 +1,67 @@
+// peer.cuh -- one-shot all-reduce of small fp64 vectors over NVLink peer memory, callable from inside a kernel.
+//
+// Every rank owns an exchange buffer [2 sequence flags, 128 B apart][2 slots x kPeerCap doubles] that all peers
+// have mapped with cudaIpc (comm.cu).  peer_exchange_block() is executed by ONE thread block per rank:
+// publish the vector in slot (call number & 1), raise the flag (st.release.sys), poll the peers' flags
+// (ld.acquire.sys through NVSwitch), add the peers' vectors in rank order (bitwise identical on all ranks).
+// A rank can be at most one call ahead of a peer -- it needs the peer's flag of the previous call to get
+// there -- so two slots are enough and no slot is overwritten while a peer still reads it.
+// The BatchNorm kernels call it between their statistics and apply phases (bn.cu), which makes the per-layer
+// statistics all-reduce part of the kernel that produces and consumes the sums instead of a separate
+// NCCL launch between two kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b2s {
+
+constexpr int kPeerMax = 8;            // GPUs of one box
+constexpr int kPeerCap = 4096;         // doubles per slot
+constexpr int kPeerFlagBytes = 256;    // two 8-byte sequence flags, 128 bytes apart
+
+struct PeerCtx {
+    const double* data[kPeerMax];      // every rank's exchange data (own = local pointer), [2 slots][kPeerCap]
+    const unsigned long long* flag[kPeerMax];
+    double* own_data;
+    unsigned long long* own_flag;
+    unsigned long long* seq;           // device-resident call counter (graph replays advance it)
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// buf[0..n) <- sum over ranks of buf[0..n); all threads of the calling block take part (n <= kPeerCap)
+__device__ __forceinline__ void peer_exchange_block(double* buf, const int n, const PeerCtx& ctx) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x, nth = blockDim.x * blockDim.y;
+    const unsigned long long seq = *((volatile unsigned long long*)ctx.seq) + 1;
+    const int slot = (int)(seq & 1);
+    double* mine = ctx.own_data + (size_t)slot * kPeerCap;
+    for (int i = tid; i < n; i += nth) mine[i] = __ldcg(buf + i);
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) st_release_sys(ctx.own_flag + slot * 16, seq);
+    if (tid < ctx.world && tid != ctx.rank) {
+        const unsigned long long* f = ctx.flag[tid] + slot * 16;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > 8000000000LL) { asm volatile("trap;"); }      // a lost peer becomes an error, not a hang
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) {
+        double s = 0.0;
+        for (int r = 0; r < ctx.world; ++r) s += __ldcv(ctx.data[r] + (size_t)slot * kPeerCap + i);
+        buf[i] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *ctx.seq = seq;
+}
+
+}  // namespace b2s

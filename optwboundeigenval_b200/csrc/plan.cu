@@ -260,6 +260,7 @@ static BnArgs bn_args(b2s_plan* p, int oi, int K) {
     a.count = (long long)p->batch * p->world * a.HW;
     a.accumulate = (op.flags & B2S_F_BWD_ACC) ? 1 : 0;
     a.pgrad_scale = 1.0f / (float)p->world;
+    a.peer = (p->comm && 2 * a.C <= 4096) ? comm_peer_ctx(p->comm) : nullptr;
     return a;
 }
 
@@ -318,7 +319,7 @@ static int forward(b2s_plan* p, int K) {
             const BnArgs a = bn_args(p, (int)oi, K);
             const int do_stats = !(first && K > 0);
             int rc = 1;
-            if (!p->comm && p->bn_fused) rc = launch_bn_fwd_fused(st, K, a, do_stats);
+            if ((!p->comm || a.peer) && p->bn_fused) rc = launch_bn_fwd_fused(st, K, a, do_stats);
             if (rc < 0) return rc;
             if (rc == 1) {
                 if (do_stats) {
@@ -441,7 +442,7 @@ static int backward(b2s_plan* p, int K) {
         case B2S_OP_BN: {
             const BnArgs a = bn_args(p, oi, K);
             int rc = 1;
-            if (!p->comm && p->bn_fused) rc = launch_bn_bwd_fused(st, K, a);
+            if ((!p->comm || a.peer) && p->bn_fused) rc = launch_bn_bwd_fused(st, K, a);
             if (rc < 0) return rc;
             if (rc == 1) {
                 B2S_TRY(launch_bn_bwd_stats(st, K, a));
@@ -1294,6 +1295,20 @@ int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world)
     p->world = world;
     if (world <= 1) return 0;
     return comm_init(&p->comm, h_id128, rank, world);
+}
+int b2s_comm_peer_local(b2s_plan* p, void* h_handle64) {
+    if (!p || !h_handle64) { set_error("b2s_comm_peer_local: null argument"); return -1; }
+    if (!p->comm) { set_error("b2s_comm_peer_local: call b2s_comm_init first"); return -1; }
+    B2S_CUDA(cudaSetDevice(p->device));
+    return comm_peer_local(p->comm, h_handle64);
+}
+int b2s_comm_peer_attach(b2s_plan* p, const void* h_handles) {
+    if (!p || !h_handles) { set_error("b2s_comm_peer_attach: null argument"); return -1; }
+    if (!p->comm) { set_error("b2s_comm_peer_attach: call b2s_comm_init first"); return -1; }
+    B2S_CUDA(cudaSetDevice(p->device));
+    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
+    return comm_peer_attach(p->comm, h_handles);
 }
 int b2s_comm_destroy(b2s_plan* p) {
     if (!p) return 0;

@@ -224,6 +224,15 @@ class SpectralPlan:
         raw = bytes(uid.cpu().numpy().tobytes())
         _lib.check(self.lib.b2s_comm_init(self.handle, ctypes.c_char_p(raw), rank, world), "b2s_comm_init")
         self.world, self.rank = world, rank
+        # exchange buffers for the one-shot peer all-reduce of the per-layer BatchNorm sums (NVLink peer memory)
+        if dist.get_backend() == "nccl" and world <= 8:
+            mine = (ctypes.c_char * 64)()
+            _lib.check(self.lib.b2s_comm_peer_local(self.handle, mine), "b2s_comm_peer_local")
+            h = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone().to(self.device)
+            hs = [torch.empty_like(h) for _ in range(world)]
+            dist.all_gather(hs, h)
+            allh = b"".join(bytes(t.cpu().numpy().tobytes()) for t in hs)
+            _lib.check(self.lib.b2s_comm_peer_attach(self.handle, ctypes.c_char_p(allh)), "b2s_comm_peer_attach")
 
 
 # one plan per live model (keyed by identity); new operators per minibatch reuse it (opt.py:424
