@@ -308,9 +308,15 @@ __device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_s
 }
 
 
-template <int K, int VEC> __global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) { bn_fwd_stats_body<K, VEC>(a); }
+template <int K, int VEC> __global__ void __launch_bounds__(256) bn_fwd_stats_kernel(const BnArgs a) {
+    bn_fwd_stats_body<K, VEC>(a);
+    if (a.peer_tail) peer_exchange_tail(a.fsum[K], 2 * a.C, *a.peer_tail);     // data parallel: all-reduce in the kernel's tail
+}
 template <int K, int VEC> __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const BnArgs a) { bn_fwd_apply_body<K, VEC>(a); }
-template <int K, int VEC> __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) { bn_bwd_stats_body<K, VEC>(a); }
+template <int K, int VEC> __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const BnArgs a) {
+    bn_bwd_stats_body<K, VEC>(a);
+    if (a.peer_tail) peer_exchange_tail(a.bsum[K], 2 * a.C, *a.peer_tail);
+}
 template <int K, int VEC> __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, float ps) { bn_bwd_apply_body<K, VEC>(a, ps); }
 
 // statistics + apply in ONE cooperative launch (grid-wide barrier between the two phases): halves the

@@ -59,6 +59,7 @@ struct Comm {
     void* xbuf = nullptr;              // [flags 256 B][2 x kPeerCap doubles]
     void* peer_base[kPeerMax] = {};
     unsigned long long* d_seq = nullptr;
+    unsigned int* d_ticket = nullptr;
     bool peers_ready = false;
     PeerCtx ctx = {};
     PeerCtx* d_ctx = nullptr;          // device copy for kernels that do the exchange themselves (bn.cu)
@@ -105,6 +106,7 @@ int comm_destroy(Comm* c) {
         if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->xbuf) cudaFree(c->xbuf);
     if (c->d_seq) cudaFree(c->d_seq);
+    if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_ctx) cudaFree(c->d_ctx);
     NcclApi* a = nccl();
     if (a && c->comm) a->CommDestroy(c->comm);
@@ -132,6 +134,8 @@ int comm_peer_local(Comm* c, void* h_handle64) {
         B2S_CUDA(cudaMemset(c->xbuf, 0, bytes));
         B2S_CUDA(cudaMalloc(&c->d_seq, sizeof(unsigned long long)));
         B2S_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
+        B2S_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
+        B2S_CUDA(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
         B2S_CUDA(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
@@ -165,6 +169,7 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
     x.own_flag = reinterpret_cast<unsigned long long*>(c->xbuf);
     x.own_data = reinterpret_cast<double*>(static_cast<char*>(c->xbuf) + kPeerFlagBytes);
     x.seq = c->d_seq;
+    x.ticket = c->d_ticket;
     x.rank = c->rank; x.world = c->world;
     if (!c->d_ctx) B2S_CUDA(cudaMalloc(&c->d_ctx, sizeof(PeerCtx)));
     B2S_CUDA(cudaMemcpy(c->d_ctx, &x, sizeof(PeerCtx), cudaMemcpyHostToDevice));
@@ -178,6 +183,13 @@ const PeerCtx* comm_peer_ctx(Comm* c) {
     // one-CTA exchange kernel between the statistics and apply kernels 3.33 ms, NCCL 3.35 ms -- the in-kernel form
     // idles the whole grid across two grid barriers while one block talks to the peers.  Opt-in: B2S_PEER_FUSED=1.
     static const bool on = getenv("B2S_PEER_FUSED") && atoi(getenv("B2S_PEER_FUSED")) != 0;
+    return (c && c->peers_ready && on) ? c->d_ctx : nullptr;
+}
+
+const PeerCtx* comm_peer_tail_ctx(Comm* c) {
+    // measured at 2 GPUs: 3.39 ms per step with the exchange in the statistics kernel's tail, 3.36 ms with the
+    // separate one-block kernel -- no gain, so the simpler form is the default.  Opt-in: B2S_PEER_TAIL=1.
+    static const bool on = getenv("B2S_PEER_TAIL") && atoi(getenv("B2S_PEER_TAIL")) != 0;
     return (c && c->peers_ready && on) ? c->d_ctx : nullptr;
 }
 

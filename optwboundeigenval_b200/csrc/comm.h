@@ -24,4 +24,6 @@ int comm_peer_attach(Comm* c, const void* h_handles);           // world x 64 by
 struct PeerCtx;
 // device-resident exchange context for kernels that do the exchange themselves (peer.cuh), NULL when unavailable
 const PeerCtx* comm_peer_ctx(Comm* c);
+// ... for reduction kernels whose last block performs the exchange (peer_exchange_tail), NULL when unavailable
+const PeerCtx* comm_peer_tail_ctx(Comm* c);
 }  // namespace b2s

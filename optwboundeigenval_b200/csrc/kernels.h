@@ -81,6 +81,7 @@ struct BnArgs {
     float pgrad_scale;        // 1/world when the sums were all-reduced (the flat vector is summed again later)
     double* csum;             // third-order compatibility sweep: [bn_corr_sums()][C]
     const struct PeerCtx* peer;   // multi-GPU: exchange context for the in-kernel all-reduce of the sums (peer.cuh), else NULL
+    const struct PeerCtx* peer_tail;   // multi-GPU: the statistics kernels' last block all-reduces the sums, else NULL
 };
 int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a);

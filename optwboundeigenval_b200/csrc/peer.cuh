@@ -24,6 +24,7 @@ struct PeerCtx {
     double* own_data;
     unsigned long long* own_flag;
     unsigned long long* seq;           // device-resident call counter (graph replays advance it)
+    unsigned int* ticket;              // arrival counter of the kernel whose last block performs the exchange
     int rank, world;
 };
 
@@ -62,6 +63,26 @@ __device__ __forceinline__ void peer_exchange_block(double* buf, const int n, co
     __threadfence();
     __syncthreads();
     if (tid == 0) *ctx.seq = seq;
+}
+
+// Tail of a reduction kernel whose blocks have just added their partial sums into `sums` with atomics: the block
+// that arrives last (ticket) all-reduces the sums over the GPUs before the kernel ends, so the statistics
+// all-reduce costs no launch of its own.  Every thread of every block must call it.
+__device__ __forceinline__ void peer_exchange_tail(double* sums, const int n, const PeerCtx& ctx) {
+    __shared__ int is_last;
+    __threadfence();                    // this block's atomics are visible device-wide before its ticket
+    __syncthreads();
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(ctx.ticket, 1u);
+        is_last = t == gridDim.x * gridDim.y * gridDim.z - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        if (tid == 0) *ctx.ticket = 0;  // kernels that use the ticket are serialised on one stream
+        __threadfence();
+        peer_exchange_block(sums, n, ctx);
+    }
 }
 
 }  // namespace b2s

@@ -261,6 +261,7 @@ static BnArgs bn_args(b2s_plan* p, int oi, int K) {
     a.accumulate = (op.flags & B2S_F_BWD_ACC) ? 1 : 0;
     a.pgrad_scale = 1.0f / (float)p->world;
     a.peer = (p->comm && 2 * a.C <= 4096) ? comm_peer_ctx(p->comm) : nullptr;
+    a.peer_tail = (p->comm && 2 * a.C <= 4096) ? comm_peer_tail_ctx(p->comm) : nullptr;
     return a;
 }
 
@@ -324,7 +325,7 @@ static int forward(b2s_plan* p, int K) {
             if (rc == 1) {
                 if (do_stats) {
                     B2S_TRY(launch_bn_fwd_stats(st, K, a));
-                    if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.fsum[K], 2 * a.C, st));
+                    if (p->comm && !a.peer_tail) B2S_TRY(comm_allreduce_f64(p->comm, a.fsum[K], 2 * a.C, st));
                 }
                 B2S_TRY(launch_bn_fwd_apply(st, K, a));
             }
@@ -446,7 +447,7 @@ static int backward(b2s_plan* p, int K) {
             if (rc < 0) return rc;
             if (rc == 1) {
                 B2S_TRY(launch_bn_bwd_stats(st, K, a));
-                if (p->comm) B2S_TRY(comm_allreduce_f64(p->comm, a.bsum[K], 2 * a.C, st));
+                if (p->comm && !a.peer_tail) B2S_TRY(comm_allreduce_f64(p->comm, a.bsum[K], 2 * a.C, st));
                 B2S_TRY(launch_bn_bwd_apply(st, K, a));
             }
             break;
