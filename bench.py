@@ -46,38 +46,67 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi SM clocks / throttle reasons while the timed region runs"""
+    """samples SM clocks / throttle reasons while the timed region runs: NVML (about 1 ms per sample) when the
+    bindings are importable, else nvidia-smi (about 100 ms per sample)"""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]          # nvmlClocksEventReason*: HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.mhz = []
+        self.max_mhz = None
+        self.seen = set()
         self.stop_flag = False
+        self.source = "nvidia-smi"
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.mhz.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            for n, b in zip(self.NAMES, self.BITS):
+                if mask & b:
+                    self.seen.add(n)
+            time.sleep(0.002)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
+                parts = [x.strip() for x in out.strip().split(",")]
                 if len(parts) >= 6:
-                    self.rows.append(parts)
+                    if parts[0].replace(".", "").isdigit():
+                        self.mhz.append(float(parts[0]))
+                    if parts[1].replace(".", "").isdigit():
+                        self.max_mhz = float(parts[1])
+                    for i, n in enumerate(self.NAMES):
+                        if parts[2 + i].lower().startswith("active"):
+                            self.seen.add(n)
             except Exception:   # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:   # noqa: BLE001
+            self._run_smi()
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        if not self.mhz:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         import statistics
-        mhz = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(mhz) if mhz else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.mhz), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(self.mhz), "source": self.source}
 
 
 def _ncu_summary():
