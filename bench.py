@@ -273,6 +273,42 @@ def run_b200(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
+    # ---- second headline metric: regularised steps/sec ---------------------------------------------
+    # one step = the minibatch body of iter() (opt.py:608-699): host batch -> device, new operator, base pass,
+    # k = 20 power iterations (max_pow_iter = 20, pow_iter_eps = 0: pinned, as SURVEY 8d prescribes), penalty
+    # gradient vGHv (K = 0 so the penalty is always active), fused step assembly, SGD update.
+    reg = None
+    if not args.no_reg:
+        import contextlib
+        from optwboundeigenval_b200.spectral import SpectralState
+        st = SpectralState(model, loss, mu=0.01, K=0.0, pow_iter_eps=0.0, max_pow_iter=20, ignore_bad_vals=False)
+        opt_sgd = torch.optim.SGD(model.parameters(), lr=1e-4)
+        xh, yh = x.pin_memory(), y.pin_memory()
+        n_reg = max(3, min(args.steps, 10))
+
+        def reg_step():
+            with contextlib.redirect_stdout(sys.stderr):          # comp_rho prints the reference's warnings
+                st.regularized_step([xh.to("cuda", non_blocking=True), yh.to("cuda", non_blocking=True)], opt_sgd)
+
+        for _ in range(2):
+            reg_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(n_reg):
+            reg_step()
+        g1.record()
+        barrier()
+        ms_reg = g0.elapsed_time(g1) / n_reg
+        tr = torch.tensor([ms_reg], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        ms_reg = float(tr[0])
+        reg = {"value": world * 1e3 / ms_reg, "unit": "regularized steps/s (32-image minibatches)", "ms_per_step": ms_reg,
+               "steps": n_reg, "hvp_per_step": 20, "penalty": "mu=0.01, K=0 (active every step): base pass + 20 HVPs + vGHv + "
+               "fused step assembly + SGD update; batch copied from pinned host memory every step",
+               "h2d_bytes_per_step": int(x.numel() * 4 + y.numel() * 8), "rho": float(st.rho)}
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -342,6 +378,7 @@ def run_b200(args):
                 "clocks": sampler.summary(),
                 "roofline": roof,
                 "roofline_vector_kernels": vec,
+                "regularized_step": reg,
                 "cpu_baseline": cpu,
                 "kernel_profile_ms": {r["name"]: round(r["ms"], 4) for r in prof},
                 "lambda_max": out.lam}
@@ -361,6 +398,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vec", action="store_true", help="skip the vector-kernel HBM roofline leg")
+    ap.add_argument("--no-reg", action="store_true", help="skip the regularised-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 12)

@@ -220,6 +220,14 @@ int b2s_kfac_clear(b2s_plan* p);
 int b2s_kfac_set(b2s_plan* p, int32_t op_index, const float* d_Ainv, const float* d_Ginv);
 int b2s_kfac_apply(b2s_plan* p, const double* d_r, double* d_out);
 
+/* ---- step assembly of the regularised minibatch step (opt.py:616-639 assembly, 654-659 scatter) ----------
+ * p = grad f + coef * grad rho with coef = mu * sign (opt.py:631-639; d_gradrho NULL when g == 0, opt.py:636),
+ * written as fp64 (d_p, optional) and as the fp32 flat vector d_p32 whose slices in model.parameters() order become
+ * param.grad (the reference's per-parameter `p[i:i+n].view(s).float()` loop, opt.py:654-659).  All vectors device
+ * resident, 16-byte aligned, enqueued on `stream`. */
+int b2s_step_assemble(const double* d_gradf, const double* d_gradrho, double coef, int64_t n, double* d_p, float* d_p32,
+                      void* stream);
+
 /* ---- data parallelism (one process per GPU) ------------------------------------------- */
 int b2s_comm_unique_id(void* h_id128);                       /* 128 bytes, rank 0 */
 int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world);

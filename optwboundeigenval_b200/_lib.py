@@ -67,6 +67,7 @@ SIGNATURES = {
     "b2s_kfac_clear": (c_int32, [c_void_p]),
     "b2s_kfac_set": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
     "b2s_kfac_apply": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "b2s_step_assemble": (c_int32, [c_void_p, c_void_p, ctypes.c_double, c_int64, c_void_p, c_void_p, c_void_p]),
     "b2s_comm_unique_id": (c_int32, [c_void_p]),
     "b2s_comm_init": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
     "b2s_comm_destroy": (c_int32, [c_void_p]),

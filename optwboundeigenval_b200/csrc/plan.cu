@@ -1286,6 +1286,12 @@ int b2s_kfac_apply(b2s_plan* p, const double* d_r, double* d_out) {
 }
 
 // ---- data parallelism ---------------------------------------------------------------------------
+int b2s_step_assemble(const double* d_gradf, const double* d_gradrho, double coef, int64_t n, double* d_p, float* d_p32,
+                      void* stream) {
+    if (!d_gradf || !d_p32 || n <= 0) { set_error("b2s_step_assemble: null argument"); return -1; }
+    return launch_step_assemble((cudaStream_t)stream, d_gradf, d_gradrho, coef, (long long)n, d_p, d_p32);
+}
+
 int b2s_comm_unique_id(void* h_id128) { return comm_unique_id(h_id128); }
 int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world) {
     if (!p || !h_id128) { set_error("b2s_comm_init: null argument"); return -1; }

@@ -269,4 +269,44 @@ int launch_pi_precond_update(cudaStream_t st, PiDev* dS, long long n, const doub
     return 0;
 }
 
+// ---- step assembly of the regularised minibatch step (opt.py:616-659) ---------------------------------
+// p = grad f + coef * grad rho  (coef = mu * sign, or no grad rho at all when g == 0), written as fp64 (the
+// reference's `p`) and as the fp32 flat vector whose slices become param.grad -- one pass over 8P (+8P) bytes in,
+// 8P + 4P bytes out, instead of one slice + cast kernel per parameter tensor in a Python loop.
+__global__ void __launch_bounds__(256) step_assemble_kernel(const double* __restrict__ gf, const double* __restrict__ gr, const double coef,
+                                                            const long long n, double* __restrict__ p64, float* __restrict__ p32) {
+    const long long n2 = n >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 a = reinterpret_cast<const double2*>(gf)[i];
+        if (gr) {
+            const double2 b = reinterpret_cast<const double2*>(gr)[i];
+            a.x += coef * b.x;
+            a.y += coef * b.y;
+        }
+        if (p64) reinterpret_cast<double2*>(p64)[i] = a;
+        reinterpret_cast<float2*>(p32)[i] = make_float2((float)a.x, (float)a.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double a = gf[n - 1];
+        if (gr) a += coef * gr[n - 1];
+        if (p64) p64[n - 1] = a;
+        p32[n - 1] = (float)a;
+    }
+}
+
+int launch_step_assemble(cudaStream_t st, const double* gf, const double* gr, double coef, long long n, double* p64, float* p32) {
+    // 16-byte vector accesses need 16-byte aligned bases (torch allocations are 256-byte aligned; slices may not be)
+    if (((uintptr_t)gf | (uintptr_t)gr | (uintptr_t)p64) & 15 || ((uintptr_t)p32 & 7)) {
+        set_error("b2s_step_assemble: vectors must be 16-byte aligned");
+        return -1;
+    }
+    int blocks = cdiv(n, 256 * 4);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    step_assemble_kernel<<<blocks, 256, 0, st>>>(gf, gr, coef, n, p64, p32);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace b2s

@@ -28,5 +28,7 @@ int pi_scratch_doubles();
 // one iteration's vector work: pass A (dots) + pass B (residual, stopping test, update)
 int launch_pi_step(cudaStream_t st, PiDev* dS, long long n, const float* hv);
 int launch_pi_precond_update(cudaStream_t st, PiDev* dS, long long n, const double* Tr);
+// p64 (optional) = gf + coef * gr (gr optional), p32 = (float)p64 : the step assembly of opt.py:616-659
+int launch_step_assemble(cudaStream_t st, const double* gf, const double* gr, double coef, long long n, double* p64, float* p32);
 
 }  // namespace b2s

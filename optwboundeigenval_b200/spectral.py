@@ -110,6 +110,53 @@ def comp_g(self, data):
     self.g = np.max([0.0, self.rho - self.K, self.Kmin - self.rho])
 
 
+class _StepBuffers(object):
+    """Flat fp64 / fp32 step vectors of one model and the per-parameter views into the fp32 one (computed once:
+    the reference recomputes ``torch.prod(torch.tensor(s))`` and slices + casts per parameter on every minibatch,
+    opt.py:654-659)."""
+
+    def __init__(self, model, device):
+        self.params = list(model.parameters())
+        self.n = sum(q.numel() for q in self.params)
+        self.p64 = torch.empty(self.n, dtype=torch.float64, device=device)
+        self.p32 = torch.empty(self.n, dtype=torch.float32, device=device)
+        self.views = []
+        i = 0
+        for q in self.params:
+            self.views.append(self.p32[i:i + q.numel()].view(q.size()))
+            i += q.numel()
+
+
+def assemble_step(self, mu=None):
+    """The step assembly of iter() (opt.py:622-639, 654-659) after ``comp_g``: ``p = grad f + mu * sign * grad rho`` in one
+    fused pass (C ABI ``b2s_step_assemble``) and ``param.grad`` set to views of the flat fp32 copy.  Returns ``p`` (fp64)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    buf = getattr(self, "_step_buffers", None)
+    if buf is None or buf.params != list(self.model.parameters()):
+        buf = self._step_buffers = _StepBuffers(self.model, self.device)
+    if mu is None:
+        mu = self.mu(getattr(self, "i", 0)) if callable(self.mu) else self.mu
+    if self.hvp_op.stored_grad is not None:                                   # opt.py:624-627
+        self.gradf = self.hvp_op.stored_grad.data.to(self.device)
+    else:
+        self.gradf = torch.zeros(self.ndim, dtype=torch.float64, device=self.device)
+    coef, gr = 0.0, None
+    if self.g > 0:                                                            # opt.py:631-637
+        self.comp_gradrho()
+        sign = 1 if self.rho > self.K else -1
+        self.gradg = sign * self.gradrho if getattr(self, "keep_gradg", False) else None
+        coef, gr = float(mu) * sign, self.gradrho
+    st = torch.cuda.current_stream(self.device).cuda_stream
+    _lib.check(lib.b2s_step_assemble(ctypes.c_void_p(self.gradf.data_ptr()), ctypes.c_void_p(gr.data_ptr()) if gr is not None else None,
+                                     ctypes.c_double(coef), buf.n, ctypes.c_void_p(buf.p64.data_ptr()),
+                                     ctypes.c_void_p(buf.p32.data_ptr()), ctypes.c_void_p(st)), "b2s_step_assemble")
+    for q, view in zip(buf.params, buf.views):                               # opt.py:654-659 without the slicing / casting kernels
+        q.grad = view
+    return buf.p64
+
+
 class SpectralState(object):
     """Minimal stand-alone carrier of the attributes the three functions use -- what
     ``OptWBoundEignVal.__init__`` (opt.py:239-316) sets up -- for users (bench, tests, smoke) that
@@ -152,6 +199,17 @@ class SpectralState(object):
     def init_kfac(self, data):    # opt.py:362-382
         from .kfac import init_kfac as _init
         return _init(self, data)
+
+    assemble_step = assemble_step
+
+    def regularized_step(self, data, optimizer):
+        """One minibatch of iter() (opt.py:608-699, the pow_iter branch with a plain optimizer): comp_g, grad f,
+        penalty gradient when g > 0, fused step assembly into param.grad, optimizer.step()."""
+        self.comp_g(data)
+        optimizer.zero_grad()
+        p = self.assemble_step()
+        optimizer.step()
+        return p
 
     def step_direction(self, data):
         """The assembly of iter() (opt.py:616-639): grad f + mu * sign * grad rho."""

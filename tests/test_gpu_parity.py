@@ -388,3 +388,42 @@ def test_tensor_core_path_matches_cuda_core_path_and_oracle():
     assert rel_err(res[2][0], ref.gradient().detach().numpy()) < RTOL_VEC
     assert rel_err(res[2][1], ref.hv(v).numpy()) < RTOL_VEC
     assert rel_err(res[2][2], ref.vghv(v).numpy()) < RTOL_VEC
+
+
+def test_fused_step_assembly_matches_iter_body():
+    """opt.py:616-659: p = grad f + mu * sign * grad rho, param.grad = p[i:i+n].view(s).float() -- here one fused kernel
+    (C ABI b2s_step_assemble) and views of one flat fp32 vector."""
+    from optwboundeigenval_b200 import zoo
+    from optwboundeigenval_b200.spectral import SpectralState
+    model, loss = zoo.build("usps")
+    model.train()
+    x, y = zoo.synthetic_batch("usps", 32)
+    st = SpectralState(model, loss, mu=0.01, K=0.0, pow_iter_eps=1e-3, max_pow_iter=50, ignore_bad_vals=False)
+    st.comp_g([x, y])
+    assert st.g > 0                                        # K = 0: the penalty is active
+    p = st.assemble_step()
+    sign = 1 if st.rho > st.K else -1
+    gf, gr = st.hvp_op.stored_grad, 0.01 * sign * st.gradrho
+    want = gf + gr
+    # fp64 exact up to the rounding of one fused multiply-add (relative to the operands: the sum may cancel)
+    assert p.dtype == torch.float64 and bool(((p - want).abs() <= 1e-15 * (gf.abs() + gr.abs())).all())
+    i = 0
+    for q in model.parameters():
+        n = q.numel()
+        assert q.grad.dtype == torch.float32 and q.grad.shape == q.shape
+        assert torch.equal(q.grad.reshape(-1), p[i:i + n].float())          # the fp32 copy is the rounding of the fp64 p
+        i += n
+    # the views alias one flat buffer: no per-parameter copies
+    base = st._step_buffers.p32
+    assert all(base.data_ptr() <= q.grad.data_ptr() < base.data_ptr() + 4 * base.numel() for q in model.parameters())
+    # inactive penalty (g == 0): p = grad f
+    st2 = SpectralState(model, loss, mu=0.01, K=1e9, pow_iter_eps=1e-3, max_pow_iter=50, ignore_bad_vals=False)
+    st2.comp_g([x, y])
+    assert st2.g == 0
+    assert torch.equal(st2.assemble_step(), st2.hvp_op.stored_grad)
+    # a full regularised step updates the parameters exactly like torch's SGD on the reference's p
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    before = torch.cat([q.detach().reshape(-1).clone() for q in model.parameters()])
+    pstep = st.regularized_step([x, y], opt)
+    after = torch.cat([q.detach().reshape(-1) for q in model.parameters()])
+    assert torch.allclose(after, before - 0.1 * pstep.float(), rtol=1e-6, atol=1e-8)

@@ -5,7 +5,7 @@
 #   3. ncu --set full of the eigen-iteration vector kernels at P = 2^26
 set -u
 R=${1:-r1}
-BENCH="python bench.py --steps 5 --warmup 3 --no-cpu --no-vec"
+BENCH="python bench.py --steps 5 --warmup 3 --no-cpu --no-vec --no-reg"
 $BENCH > gpurun_out/${R}_bench_plain.json 2> gpurun_out/${R}_bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/${R}_launches_bench.csv $BENCH > gpurun_out/${R}_bench_under_ncu.log 2>&1
 echo "launch list rc $?"
