@@ -201,6 +201,11 @@ def _config(kind, batch, world):
 
 
 def run_b200(args):
+    # stdout carries exactly ONE JSON line (rank 0): everything else that writes to file descriptor 1 while the bench runs
+    # (NCCL's "NCCL version ..." banner, library warnings) is sent to stderr, the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -382,7 +387,8 @@ def run_b200(args):
                 "cpu_baseline": cpu,
                 "kernel_profile_ms": {r["name"]: round(r["ms"], 4) for r in prof},
                 "lambda_max": out.lam}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
