@@ -428,33 +428,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
                 const int n = (int)(j / HWd);
                 const int pix = (int)(j - (long long)n * HWd);
                 const int m0 = nt * BN;
-                float* __restrict__ outp = a.out + (long long)n * d_ss + pix + (long long)m0 * HWd;
-                const float* __restrict__ refp = a.relu_mode == 2 ? a.relu_ref + (long long)n * d_ss + pix + (long long)m0 * HWd : nullptr;
-                const float* __restrict__ bias = a.bias;
+                const long long off = (long long)n * d_ss + pix + (long long)m0 * HWd;
                 const int mrem = Cd - m0;                 // valid channels of this tile
-                {
-                    const bool need_out = a.accumulate != 0;
-#pragma unroll
-                    for (int i0 = 0; i0 < BN; i0 += 8) {
-                        float prev[8], ref[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool okc = i0 + i < mrem;
-                            prev[i] = (need_out && okc) ? outp[(long long)(i0 + i) * HWd] : 0.f;
-                            ref[i] = (refp && okc) ? __ldg(refp + (long long)(i0 + i) * HWd) : 1.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (i0 + i < mrem) {
-                                float val = acc[i0 + i] + prev[i];
-                                if (bias) val += __ldg(bias + m0 + i0 + i);
-                                if (a.relu_mode == 1) val = val > 0.f ? val : 0.f;
-                                else if (!(ref[i] > 0.f)) val = 0.f;
-                                outp[(long long)(i0 + i) * HWd] = val;
-                            }
-                        }
-                    }
-                }
+                tc_store_tile<BN>(acc, a, off, HWd, m0, mrem);
             }
         }
     } else {

@@ -87,53 +87,6 @@ __device__ __forceinline__ void tm_stamp(long long* trace, int role, uint32_t kb
 #endif
 }
 
-// one pixel's BN output channels: out[c] (+)= acc[c] with the ReLU variant; channel stride cs, mrem valid channels.
-// Loads (previous value, ReLU reference) are issued eight channels ahead of the stores that need them.
-template <int BN, bool ACC, int RELU>
-__device__ __forceinline__ void tm_epilogue(const float (&acc)[BN], float* __restrict__ outp, const float* __restrict__ refp,
-                                            const int cs, const int mrem) {
-    if (mrem >= BN) {                             // full tile: no per-channel predicates at all
-#pragma unroll
-        for (int i0 = 0; i0 < BN; i0 += 8) {
-            float prev[8], ref[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (ACC) prev[i] = outp[(long long)(i0 + i) * cs];
-                if (RELU == 2) ref[i] = __ldg(refp + (long long)(i0 + i) * cs);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float val = acc[i0 + i];
-                if (ACC) val += prev[i];
-                if (RELU == 1) val = fmaxf(val, 0.f);
-                if (RELU == 2) val = ref[i] > 0.f ? val : 0.f;
-                outp[(long long)(i0 + i) * cs] = val;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i0 = 0; i0 < BN; i0 += 8) {
-            float prev[8], ref[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool okc = i0 + i < mrem;
-                if (ACC) prev[i] = okc ? outp[(long long)(i0 + i) * cs] : 0.f;
-                if (RELU == 2) ref[i] = okc ? __ldg(refp + (long long)(i0 + i) * cs) : 1.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i0 + i < mrem) {
-                    float val = acc[i0 + i];
-                    if (ACC) val += prev[i];
-                    if (RELU == 1) val = fmaxf(val, 0.f);
-                    if (RELU == 2) val = ref[i] > 0.f ? val : 0.f;
-                    outp[(long long)(i0 + i) * cs] = val;
-                }
-            }
-        }
-    }
-}
-
 template <int BN, int MODE, int PT>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const TmaTiling tg) {
@@ -338,20 +291,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                 const int m0 = nt * BN;
                 const long long off = (long long)n * d_ss + pix + (long long)m0 * HWd;
                 const int mrem = Cd - m0;                 // valid channels of this tile
-                if (a.bias) {
-#pragma unroll
-                    for (int i = 0; i < BN; ++i)
-                        if (i < mrem) acc[i] += __ldg(a.bias + m0 + i);
-                }
-                const int variant = (a.accumulate != 0 ? 1 : 0) + 2 * a.relu_mode;
-                switch (variant) {
-                case 0: tm_epilogue<BN, false, 0>(acc, a.out + off, nullptr, HWd, mrem); break;
-                case 1: tm_epilogue<BN, true, 0>(acc, a.out + off, nullptr, HWd, mrem); break;
-                case 2: tm_epilogue<BN, false, 1>(acc, a.out + off, nullptr, HWd, mrem); break;
-                case 3: tm_epilogue<BN, true, 1>(acc, a.out + off, nullptr, HWd, mrem); break;
-                case 4: tm_epilogue<BN, false, 2>(acc, a.out + off, a.relu_ref + off, HWd, mrem); break;
-                default: tm_epilogue<BN, true, 2>(acc, a.out + off, a.relu_ref + off, HWd, mrem); break;
-                }
+                tc_store_tile<BN>(acc, a, off, HWd, m0, mrem);
             }
         }
     } else {
