@@ -284,35 +284,38 @@ def run_b200(args):
     # gradient vGHv (K = 0 so the penalty is always active), fused step assembly, SGD update.
     reg = None
     if not args.no_reg:
-        import contextlib
-        from optwboundeigenval_b200.spectral import SpectralState
-        st = SpectralState(model, loss, mu=0.01, K=0.0, pow_iter_eps=0.0, max_pow_iter=20, ignore_bad_vals=False)
-        opt_sgd = torch.optim.SGD(model.parameters(), lr=1e-4)
-        xh, yh = x.pin_memory(), y.pin_memory()
-        n_reg = max(3, min(args.steps, 10))
+        try:
+            import contextlib
+            from optwboundeigenval_b200.spectral import SpectralState
+            st = SpectralState(model, loss, mu=0.01, K=0.0, pow_iter_eps=0.0, max_pow_iter=20, ignore_bad_vals=False)
+            opt_sgd = torch.optim.SGD(model.parameters(), lr=1e-4)
+            xh, yh = x.pin_memory(), y.pin_memory()
+            n_reg = max(3, min(args.steps, 10))
 
-        def reg_step():
-            with contextlib.redirect_stdout(sys.stderr):          # comp_rho prints the reference's warnings
-                st.regularized_step([xh.to("cuda", non_blocking=True), yh.to("cuda", non_blocking=True)], opt_sgd)
+            def reg_step():
+                with contextlib.redirect_stdout(sys.stderr):          # comp_rho prints the reference's warnings
+                    st.regularized_step([xh.to("cuda", non_blocking=True), yh.to("cuda", non_blocking=True)], opt_sgd)
 
-        for _ in range(2):
-            reg_step()
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(n_reg):
-            reg_step()
-        g1.record()
-        barrier()
-        ms_reg = g0.elapsed_time(g1) / n_reg
-        tr = torch.tensor([ms_reg], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-        ms_reg = float(tr[0])
-        reg = {"value": world * 1e3 / ms_reg, "unit": "regularized steps/s (32-image minibatches)", "ms_per_step": ms_reg,
-               "steps": n_reg, "hvp_per_step": 20, "penalty": "mu=0.01, K=0 (active every step): base pass + 20 HVPs + vGHv + "
-               "fused step assembly + SGD update; batch copied from pinned host memory every step",
-               "h2d_bytes_per_step": int(x.numel() * 4 + y.numel() * 8), "rho": float(st.rho)}
+            for _ in range(2):
+                reg_step()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(n_reg):
+                reg_step()
+            g1.record()
+            barrier()
+            ms_reg = g0.elapsed_time(g1) / n_reg
+            tr = torch.tensor([ms_reg], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            ms_reg = float(tr[0])
+            reg = {"value": world * 1e3 / ms_reg, "unit": "regularized steps/s (32-image minibatches)", "ms_per_step": ms_reg,
+                   "steps": n_reg, "hvp_per_step": 20, "penalty": "mu=0.01, K=0 (active every step): base pass + 20 HVPs + vGHv + "
+                   "fused step assembly + SGD update; batch copied from pinned host memory every step",
+                   "h2d_bytes_per_step": int(x.numel() * 4 + y.numel() * 8), "rho": float(st.rho)}
+        except Exception as e:   # noqa: BLE001  (the headline line must survive a failure of this extra leg)
+            reg = {"error": repr(e)}
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
