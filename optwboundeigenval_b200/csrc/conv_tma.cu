@@ -67,6 +67,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 // returns at once, so that a protocol error ends the kernel with a diagnosis instead of a trap
 __device__ unsigned int tm_timeout_flag = 0;
 __device__ __forceinline__ void tm_wait(uint64_t* bar, uint32_t parity, int dbg, unsigned id) {
+    if (dbg & 8) { mbar_wait_spin(bar, parity); return; }          // experiment: spin instead of NANOSLEEP.SYNCS
     if (!(dbg & 4)) { mbar_wait(bar, parity); return; }
     const uint32_t addr = smem_u32(bar);
     if (*((volatile unsigned int*)&tm_timeout_flag)) return;
@@ -304,6 +305,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
             const uint64_t desc0 = umma_desc(smem_u32(bbuf), 128, 1024);         // stage 0, hi tile, k-step 0
             constexpr int NACC = tc_nacc(BN);
             uint32_t kbg = 0, grp = 0;
+            const int mma_spin = (tg.dbg & 16) ? 8 : 0;           // B2S_TMA_DBG bit 4: the MMA issuer spins on its barriers
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int p = 0; p < a.npairs; ++p) {
                     int kbl = 0;
@@ -319,9 +321,9 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                                 const bool first = (kbl % TM_G) == 0;
                                 const bool last = (kbl % TM_G) == TM_G - 1 || kbl == KBp - 1;
                                 if (lane == 0) tm_stamp(a.trace, 1, kbg, 0);
-                                tm_wait(&a_full[s], round & 1, dbg, 400 + s);
+                                tm_wait(&a_full[s], round & 1, dbg | mma_spin, 400 + s);
                                 if (lane == 0) tm_stamp(a.trace, 1, kbg, 1);
-                                if (first && use > 0) tm_wait(&d_empty[b], (use - 1) & 1, dbg, 500 + b);
+                                if (first && use > 0) tm_wait(&d_empty[b], (use - 1) & 1, dbg | mma_spin, 500 + b);
                                 __syncwarp();
                                 tc_fence_after();
                                 if (lane == 0) tm_stamp(a.trace, 1, kbg, 2);
@@ -488,7 +490,7 @@ static int launch_tma_t(cudaStream_t st, const ConvKArgs& a, const TmaMaps& maps
         const cudaError_t e = launch_pdl(conv_tma_kernel<BN, MODE, PT>, dim3(grid), dim3(TM_THREADS), smem, st, a, maps, tg);
         if (e != cudaSuccess) { set_error("conv_tma launch: %s", cudaGetErrorString(e)); return -3; }
     }
-    if (tg.dbg) {
+    if (tg.dbg & 7) {
         const cudaError_t e = cudaStreamSynchronize(st);
         unsigned flag = 0;
         cudaMemcpyFromSymbol(&flag, tm_timeout_flag, sizeof(flag));
