@@ -24,6 +24,8 @@ SOURCES = ["plan.cu", "conv.cu", "bn.cu", "elementwise.cu", "head.cu", "vec.cu",
            "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tma.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("B2S_BUILD_TRUNC"):          # experiment: truncating TF32 split in conv_tma.cu
+    CFLAGS.append("-DB2S_TMA_TRUNC")
 if os.environ.get("B2S_BUILD_TRACE"):          # per-role clock stamps in the tcgen05 kernel (tools/tc_trace.py)
     CFLAGS.append("-DB2S_TC_TRACE_ENABLED")
 

@@ -202,7 +202,11 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                                         // lo = f - hi is exact in fp32 (<= 12 significant bits); the tensor core
                                         // reads its upper 19 bits
                                         const float f = v[j * 8 + i];
+#ifdef B2S_TMA_TRUNC                     // experiment (B2S_BUILD_TRUNC=1): truncating split, one ALU instruction less per element
+                                        hi[i] = __float_as_uint(f) & 0xffffe000u;
+#else
                                         hi[i] = (__float_as_uint(f) + 0x1000u) & 0xffffe000u;
+#endif
                                         lo[i] = __float_as_uint(f - __uint_as_float(hi[i]));
                                     }
                                     tmem_st8(lane_addr + col + j * 8, hi);
