@@ -238,6 +238,17 @@ class SpectralPlan:
 # one plan per live model (keyed by identity); new operators per minibatch reuse it (opt.py:424
 # constructs a new HVPOperator for every batch)
 _PLANS = {}
+_DATA_PARALLEL = True
+
+
+def set_data_parallel(on: bool):
+    """True (default): a minibatch is sharded over the ranks of torch.distributed (synced BatchNorm sums, all-reduced
+    results).  False: *replicas only* -- every rank works on its own minibatches with no collective at all (the
+    ``rho_test`` sweep, opt.py:882-910).  Changing the mode drops the cached plans."""
+    global _DATA_PARALLEL
+    if bool(on) != _DATA_PARALLEL:
+        _DATA_PARALLEL = bool(on)
+        _PLANS.clear()
 
 
 def plan_for(model, criterion, x: torch.Tensor, device, max_batch=None) -> SpectralPlan:
@@ -250,7 +261,7 @@ def plan_for(model, criterion, x: torch.Tensor, device, max_batch=None) -> Spect
         if ref() is model and plan.max_batch >= batch and plan.device == device:
             return plan
     plan = SpectralPlan(model, criterion, shape, max(batch, max_batch or 0), device)
-    if torch.distributed.is_available() and torch.distributed.is_initialized():
+    if _DATA_PARALLEL and torch.distributed.is_available() and torch.distributed.is_initialized():
         plan.init_comm()
     _PLANS[key] = (weakref.ref(model), plan)
     return plan

@@ -110,6 +110,46 @@ def comp_g(self, data):
     self.g = np.max([0.0, self.rho - self.K, self.Kmin - self.rho])
 
 
+def rho_test(self, loader, replicas=True):
+    """``OptWBoundEignVal.rho_test`` (opt.py:882-910): lambda_max of every minibatch of ``loader`` and the batch-size
+    weighted averages of ``[rho, norm, iterations, rn, seconds]``.
+
+    With ``torch.distributed`` initialised and ``replicas=True`` the sweep is *replicas only*: rank r takes the
+    minibatches j with j % world == r, runs the single-GPU path on them (no synced BatchNorm, no all-reduce: every
+    minibatch is a whole batch on one GPU, exactly as in the reference) and the per-batch rows are gathered at the
+    end -- the path has no exchange step, so none is invented.  Returns ``(stats, averages)``; every rank gets both."""
+    import torch.distributed as dist
+    from . import hvp_operator
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    sharded = world > 1 and replicas
+    if sharded:
+        hvp_operator.set_data_parallel(False)
+    try:
+        rows, sizes = [], []
+        for j, data in enumerate(loader):
+            if sharded and j % world != rank:
+                continue
+            start = time.time()
+            i, rn, size = self.comp_rho(data)
+            rows.append([j, float(self.rho), float(self.norm), int(i), float(rn), time.time() - start])
+            sizes.append(int(size))
+    finally:
+        if sharded:
+            hvp_operator.set_data_parallel(True)
+    if sharded:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (rows, sizes))
+        rows = [r for part in gathered for r in part[0]]
+        sizes = [z for part in gathered for z in part[1]]
+        order = np.argsort([r[0] for r in rows], kind="stable")
+        rows = [rows[k] for k in order]
+        sizes = [sizes[k] for k in order]
+    stats = np.array(rows, dtype="float")
+    avg = np.average(stats, axis=0, weights=sizes)[1:] if len(rows) else np.zeros(5)
+    return stats, avg
+
+
 class _StepBuffers(object):
     """Flat fp64 / fp32 step vectors of one model and the per-parameter views into the fp32 one (computed once:
     the reference recomputes ``torch.prod(torch.tensor(s))`` and slices + casts per parameter on every minibatch,
@@ -201,6 +241,7 @@ class SpectralState(object):
         return _init(self, data)
 
     assemble_step = assemble_step
+    rho_test = rho_test
 
     def regularized_step(self, data, optimizer):
         """One minibatch of iter() (opt.py:608-699, the pow_iter branch with a plain optimizer): comp_g, grad f,

@@ -427,3 +427,22 @@ def test_fused_step_assembly_matches_iter_body():
     pstep = st.regularized_step([x, y], opt)
     after = torch.cat([q.detach().reshape(-1) for q in model.parameters()])
     assert torch.allclose(after, before - 0.1 * pstep.float(), rtol=1e-6, atol=1e-8)
+
+
+def test_rho_test_sweep_matches_per_batch_comp_rho():
+    """opt.py:882-910: rho of every minibatch of a loader and the size-weighted averages."""
+    from optwboundeigenval_b200 import zoo
+    from optwboundeigenval_b200.spectral import SpectralState
+    model, loss = zoo.build("usps")
+    model.train()
+    batches = [zoo.synthetic_batch("usps", b, seed=zoo.SEED + k) for k, b in enumerate((32, 16, 32))]   # ragged loader
+    st = SpectralState(model, loss, pow_iter_eps=1e-3, max_pow_iter=200, ignore_bad_vals=False, rand_init=True)
+    stats, avg = st.rho_test(batches)
+    assert stats.shape == (3, 6) and list(stats[:, 0]) == [0.0, 1.0, 2.0]
+    want = []
+    for data in batches:
+        i, rn, size = st.comp_rho(data)
+        want.append([st.rho, st.norm, i, rn])
+    want = np.array(want, dtype="float")
+    np.testing.assert_allclose(stats[:, 1:5], want, rtol=1e-6, atol=0)
+    np.testing.assert_allclose(avg[:4], np.average(want, axis=0, weights=[32, 16, 32]), rtol=1e-6)
