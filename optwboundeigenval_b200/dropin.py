@@ -43,6 +43,10 @@ def install(opt_module, fused_loop: bool = True, force_gpu: bool = True):
         cls.comp_gradrho = spectral.comp_gradrho
         cls.kfac = _kfac.kfac
         cls.init_kfac = _kfac.init_kfac
+        # additions (no reference method is replaced): the fused step assembly of iter()'s minibatch body and the
+        # replicas-only multi-GPU form of the rho_test sweep
+        cls.assemble_step = spectral.assemble_step
+        cls.rho_sweep = spectral.rho_test
     if force_gpu:
         orig_init = cls.__init__
 
@@ -75,6 +79,9 @@ def uninstall(opt_module):
     cls.comp_rho, cls.comp_gradrho, cls.__init__ = saved["comp_rho"], saved["comp_gradrho"], saved["__init__"]
     if "kfac" in saved:
         cls.kfac, cls.init_kfac = saved["kfac"], saved["init_kfac"]
+        for extra in ("assemble_step", "rho_sweep"):
+            if extra in cls.__dict__:
+                delattr(cls, extra)
     del opt_module._b200_saved
 
 
