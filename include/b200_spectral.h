@@ -239,6 +239,10 @@ int b2s_comm_destroy(b2s_plan* p);
  * (or when peer access is unavailable) every all-reduce stays on NCCL. */
 int b2s_comm_peer_local(b2s_plan* p, void* h_handle64);
 int b2s_comm_peer_attach(b2s_plan* p, const void* h_handles /* world x 64 bytes, rank order */);
+/* 1 when this rank mapped every peer.  The ranks must agree: the host side all-reduces (min) the flags and calls
+ * b2s_comm_peer_disable everywhere when one rank could not attach (mixed NCCL / peer ranks would dead-lock). */
+int b2s_comm_peer_ready(const b2s_plan* p);
+int b2s_comm_peer_disable(b2s_plan* p);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ SIGNATURES = {
     "b2s_comm_destroy": (c_int32, [c_void_p]),
     "b2s_comm_peer_local": (c_int32, [c_void_p, c_void_p]),
     "b2s_comm_peer_attach": (c_int32, [c_void_p, c_void_p]),
+    "b2s_comm_peer_ready": (c_int32, [c_void_p]),
+    "b2s_comm_peer_disable": (c_int32, [c_void_p]),
 }
 
 _lib = None

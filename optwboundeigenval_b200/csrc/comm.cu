@@ -178,6 +178,9 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
     return 0;
 }
 
+int comm_peer_ready(const Comm* c) { return (c && c->peers_ready) ? 1 : 0; }
+void comm_peer_disable(Comm* c) { if (c) c->peers_ready = false; }
+
 const PeerCtx* comm_peer_ctx(Comm* c) {
     // measured at 2 GPUs (DenseNet3): exchange inside the cooperative BatchNorm kernel 3.60 ms per step, separate
     // one-CTA exchange kernel between the statistics and apply kernels 3.33 ms, NCCL 3.35 ms -- the in-kernel form

@@ -21,6 +21,10 @@ int comm_allreduce_f64(Comm* c, double* buf, long long n, cudaStream_t st);
 // for n <= the exchange capacity once the peers are attached, NCCL otherwise.
 int comm_peer_local(Comm* c, void* h_handle64);                 // allocate the exchange buffer, return its IPC handle
 int comm_peer_attach(Comm* c, const void* h_handles);           // world x 64 bytes, rank order
+// whether this rank mapped every peer; all ranks must agree before the peer path is used (hvp_operator.init_comm
+// all-reduces the flags and disables the path everywhere when one rank could not attach)
+int comm_peer_ready(const Comm* c);
+void comm_peer_disable(Comm* c);
 struct PeerCtx;
 // device-resident exchange context for kernels that do the exchange themselves (peer.cuh), NULL when unavailable
 const PeerCtx* comm_peer_ctx(Comm* c);

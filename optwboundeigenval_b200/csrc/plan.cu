@@ -1317,6 +1317,14 @@ int b2s_comm_peer_attach(b2s_plan* p, const void* h_handles) {
     p->graphs.clear();
     return comm_peer_attach(p->comm, h_handles);
 }
+int b2s_comm_peer_ready(const b2s_plan* p) { return (p && p->comm) ? comm_peer_ready(p->comm) : 0; }
+int b2s_comm_peer_disable(b2s_plan* p) {
+    if (!p || !p->comm) return 0;
+    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
+    comm_peer_disable(p->comm);
+    return 0;
+}
 int b2s_comm_destroy(b2s_plan* p) {
     if (!p) return 0;
     if (p->comm) { comm_destroy(p->comm); p->comm = nullptr; }

@@ -233,6 +233,11 @@ class SpectralPlan:
             dist.all_gather(hs, h)
             allh = b"".join(bytes(t.cpu().numpy().tobytes()) for t in hs)
             _lib.check(self.lib.b2s_comm_peer_attach(self.handle, ctypes.c_char_p(allh)), "b2s_comm_peer_attach")
+            # every rank or none: a rank that could not map its peers would use NCCL while the others poll flags
+            ok = torch.tensor([int(self.lib.b2s_comm_peer_ready(self.handle))], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                _lib.check(self.lib.b2s_comm_peer_disable(self.handle), "b2s_comm_peer_disable")
 
 
 # one plan per live model (keyed by identity); new operators per minibatch reuse it (opt.py:424
