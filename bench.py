@@ -13,17 +13,23 @@ vector algebra and stopping test; the base pass (prepare_grad) is cached exactly
 
 value   device-resident throughput: b2s_power_iterate run for exactly K iterations (eps = 0).
         With N GPUs each rank holds its own 32-image shard (weak scaling, global batch 32 N, synced
-        BatchNorm statistics, one NCCL all-reduce of the P-vector per HVP); value counts
-        32-image-minibatch HVP equivalents: N * K / time.
+        BatchNorm statistics, one all-reduce of the P-vector per HVP); value counts 32-image-minibatch
+        HVP equivalents: N * K / time (config.unit_note).
 e2e     the same HVP through the reference-facing call B200HVPOperator.Hv(vec) with a HOST vector:
         per step 8P bytes host->device (pinned) and 8P bytes device->host are inside the timed region.
-roofline / cpu_baseline: see DESIGN.md "Measurement".
---impl reference times the CPU restatement of the reference's algorithm (oracle/, nested torch.autograd
-on all host cores) on the same config; rank 0 only.
+roofline / cpu_baseline / parity / per_config / gpu_autograd_yardstick: see DESIGN.md "Measurement".
+
+--impl reference times the reference's own CPU implementation on the same config, rank 0 only: the
+UNMODIFIED reference (opt.OptWBoundEignVal.comp_rho driving opt.HVPOperator, nested torch.autograd on
+all host cores) when a checkout is present (baseline/_ref/optWBoundEigenval travels to the GPU box),
+else the oracle port.  Warm-up = the first W iterations of comp_rho's loop (they include the base
+pass), timed = the next K iterations, each with the loop's own residual / stopping-test algebra.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -33,6 +39,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+METRIC = "HVPs/sec (power-iter lambda_max)"
+UNIT = "HVP/s"
 
 
 def _peaks():
@@ -110,12 +119,13 @@ class ClockSampler(threading.Thread):
 
 
 def _ncu_summary():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)"""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_top_kernel.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return json.load(fh)
-    return None
+    """dram bytes per launch of the dominant kernels from the committed ncu --set full captures (profiles/)"""
+    for name in ("r2_ncu_top_kernel.json", "r1_ncu_top_kernel.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as fh:
+                return json.load(fh), "profiles/" + name
+    return None, None
 
 
 def vector_roofline(peaks):
@@ -129,62 +139,187 @@ def vector_roofline(peaks):
             "ms_per_iteration": r["ms_per_iteration"], "algorithmic_bytes_per_iteration": r["bytes_per_iteration"]}
 
 
-def cpu_hvp_rate(kind, batch, seconds_budget=20.0, min_calls=3):
-    """HVPs/sec of the oracle port (the reference's nested-autograd algorithm) on all host cores."""
+def measure_tf32_peak():
+    """dense TF32 matmul rate of this GPU the way MEASURED_PEAKS.json measured bf16: torch.matmul 8192^3 with
+    allow_tf32, best of 10 (library call, used only as the roofline denominator)"""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        for _ in range(3):
+            a @ b
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's own implementation (CPU, or the same stock autograd path on the GPU as a yard-stick)
+# ---------------------------------------------------------------------------------------------------------
+def _reference_objects(kind, like_model, use_gpu=False):
+    """(opt module, reference model carrying like_model's weights, reference loss) or None without a checkout"""
+    from oracle import reference_access as ra
+    if ra.find_reference() is None:
+        return None
+    opt = ra.import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, loss = ra.ref_model_with_state(kind, like_model)
+    model.train()
+    return opt, model, loss
+
+
+def reference_comp_rho_rate(kind, batch, warmup, steps, use_gpu=False):
+    """HVPs/sec inside the UNMODIFIED reference's comp_rho (opt.py:418-533): warm-up = its first `warmup`
+    iterations (incl. the base pass), timed = the next `steps` iterations.  Returns (rate, seconds, kind_str)."""
     import torch
     from optwboundeigenval_b200 import zoo
-    from oracle import autograd_oracle as ao
-    torch.set_num_threads(os.cpu_count() or 1)
-    model, loss = zoo.build(kind)
-    model.train()
+    zmodel, zloss = zoo.build(kind)
     x, y = zoo.synthetic_batch(kind, batch)
-    op = ao.AutogradSpectralOperator(model, [x, y], loss)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = _reference_objects(kind, zmodel, use_gpu)
+    n_it = warmup + steps + 1
+    if ref is None:                                   # no checkout on this machine: the oracle port
+        from oracle import autograd_oracle as ao
+        zmodel.train()
+        op = ao.AutogradSpectralOperator(zmodel, [x, y], zloss)
+        stamps = []
+
+        def hv(v):
+            stamps.append(time.time())
+            return op.hv(v)
+        P = sum(p.numel() for p in zmodel.parameters())
+        ao.power_iteration(hv, ao.start_vector(P), eps=0.0, max_iter=n_it)
+        dt = stamps[warmup + steps] - stamps[warmup]
+        return steps / dt, dt, "port"
+    opt, model, loss = ref
+    stamps = []
+
+    class Stamped(opt.HVPOperator):                   # time stamps only; the arithmetic is the reference's
+        def Hv(self, vec, storedGrad=False):
+            if use_gpu:
+                torch.cuda.synchronize()
+            stamps.append(time.time())
+            return super().Hv(vec, storedGrad)
+
+    real = opt.HVPOperator
+    opt.HVPOperator = Stamped
+    cwd = os.getcwd()
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="b2s_ref_")
+    os.makedirs(os.path.join(tmp, "logs"))
+    os.chdir(tmp)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            o = opt.OptWBoundEignVal(model, loss, torch.optim.SGD(model.parameters(), lr=0.1), mu=0.01, K=10,
+                                     pow_iter_eps=0.0, max_pow_iter=n_it, use_gpu=use_gpu, ignore_bad_vals=False,
+                                     header="bench", batch_size=batch)
+            o.comp_rho([x, y])
+    finally:
+        os.chdir(cwd)
+        opt.HVPOperator = real
+    dt = stamps[warmup + steps] - stamps[warmup]
+    return steps / dt, dt, "reference"
+
+
+def reference_gpu_hv_rate(kind, batch, warmup, steps):
+    """HVPs/sec of the UNMODIFIED opt.HVPOperator with use_gpu=True on this GPU (stock torch.autograd double backward
+    through cuBLAS / cuDNN), driven by a plain normalised power iteration.  comp_rho itself cannot be used here: its
+    np.min over two CUDA tensors (opt.py:463) does not run on a GPU."""
+    import torch
+    from optwboundeigenval_b200 import zoo
+    zmodel, _ = zoo.build(kind)
+    ref = _reference_objects(kind, zmodel, True)
+    if ref is None:
+        raise RuntimeError("no reference checkout on this machine")
+    opt, model, loss = ref
+    x, y = zoo.synthetic_batch(kind, batch)
+    op = opt.HVPOperator(model, [x, y], loss, use_gpu=True)
     P = sum(p.numel() for p in model.parameters())
-    v = ao.start_vector(P)
-    op.hv(v)                      # builds the graph (prepare_grad) + first double backward: warm-up
-    op.hv(v)
-    t0 = time.time()
-    n = 0
-    while n < min_calls or (time.time() - t0 < seconds_budget and n < 200):
-        op.hv(v)
-        n += 1
+    v = torch.full((P,), P ** -0.5, dtype=torch.float64, device="cuda")
+    t0 = 0.0
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            t0 = time.time()
+        w = op.Hv(v, storedGrad=True)
+        v = w / torch.norm(w)
+    torch.cuda.synchronize()
     dt = time.time() - t0
-    return n / dt, n, dt
+    model.cpu()
+    return steps / dt, dt
+
+
+def reference_iter_body_rate(kind, batch, n_steps=2, k=20, use_gpu=False):
+    """regularised steps/sec of the UNMODIFIED reference's iter() minibatch body (opt.py:608-699): comp_g with
+    exactly k power iterations, vGHv (K = 0: penalty active), assembly, SGD step."""
+    import torch
+    from optwboundeigenval_b200 import zoo
+    zmodel, _ = zoo.build(kind)
+    ref = _reference_objects(kind, zmodel, use_gpu)
+    if ref is None:
+        return None
+    opt, model, loss = ref
+    xs, ys = zip(*[zoo.synthetic_batch(kind, batch, seed=zoo.SEED + j) for j in range(n_steps + 1)])
+    x, y = torch.cat(xs), torch.cat(ys)
+    cwd = os.getcwd()
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="b2s_ref_")
+    os.makedirs(os.path.join(tmp, "logs"))
+    os.chdir(tmp)
+    stamps = []
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            o = opt.OptWBoundEignVal(model, loss, torch.optim.SGD(model.parameters(), lr=1e-4), mu=0.01, K=0,
+                                     pow_iter_eps=0.0, max_pow_iter=k, use_gpu=use_gpu, ignore_bad_vals=False,
+                                     header="bench_iter", batch_size=batch)
+            real_g = o.comp_g
+
+            def comp_g(data):                          # stamps the start of every minibatch body
+                stamps.append(time.time())
+                return real_g(data)
+            o.comp_g = comp_g
+            o.comp_f = lambda *a, **kw: (0.0, None)    # the epoch-end evaluation is not part of a step
+            o.dataloader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=batch)
+            o.iter()
+    finally:
+        os.chdir(cwd)
+    dt = stamps[n_steps + 1] - stamps[1]               # bodies 1..n_steps; body 0 is the warm-up, the last stamp
+    n = n_steps                                        # is the end-of-epoch comp_g(rdata) that follows them
+    return {"value": n / dt, "unit": "regularized steps/s", "steps": n, "seconds": dt, "hvp_per_step": k,
+            "cores": os.cpu_count() or 1, "kind": "reference",
+            "sample": "%d minibatch bodies of the unmodified iter() after one warm-up body" % n}
 
 
 def run_reference(args):
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from optwboundeigenval_b200 import zoo
-    from oracle import autograd_oracle as ao
     kind, batch = args.config, args.batch or zoo.CONFIGS[args.config][3]
-    torch.set_num_threads(os.cpu_count() or 1)
-    model, loss = zoo.build(kind)
-    model.train()
-    x, y = zoo.synthetic_batch(kind, batch)
-    op = ao.AutogradSpectralOperator(model, [x, y], loss)
-    P = sum(p.numel() for p in model.parameters())
-    v = ao.start_vector(P)
-    for _ in range(max(args.warmup, 1)):
-        op.hv(v)
-    t0 = time.time()
-    for _ in range(args.steps):
-        w = op.hv(v)
-        lam = float(torch.dot(w, v))
-        v = w / torch.norm(w) if lam >= 0 else -w / torch.norm(w)
-    dt = time.time() - t0
-    val = args.steps / dt
+    val, dt, how = reference_comp_rho_rate(kind, batch, args.warmup, args.steps)
     cores = os.cpu_count() or 1
-    line = {"impl": "reference", "metric": "HVPs/sec (power-iter lambda_max)", "value": val, "unit": "HVP/s",
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(kind, batch, 1),
-            "cpu_baseline": {"value": val, "unit": "HVP/s", "cores": cores, "kind": "port",
-                             "sample": "%d power-iteration HVPs of one %d-image minibatch (oracle/autograd_oracle.py, "
-                                       "nested torch.autograd on CPU, torch threads = %d)" % (args.steps, batch, cores)},
-            "e2e": {"value": val, "unit": "HVP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": how,
+                             "sample": "iterations %d..%d of comp_rho's loop on one %d-image minibatch (%s, nested "
+                                       "torch.autograd on CPU, torch threads = %d)" % (
+                                           args.warmup, args.warmup + args.steps - 1, batch,
+                                           "unmodified opt.OptWBoundEignVal.comp_rho + opt.HVPOperator" if how == "reference"
+                                           else "oracle/autograd_oracle.py", cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -195,9 +330,62 @@ def _config(kind, batch, world):
              "chest_vgg": "params/chestxray_mu0_001_K0_vgg.py: VGG16-bn chest model, 224x224 synthetic",
              "chest_densenet121": "params/chestxray_best_reg.py: DenseNet121 chest model, 224x224 synthetic"}
     return {"workload": names[kind], "batch_per_gpu": batch, "global_batch": batch * world,
-            "parallelism": "dp%d (minibatch sharded, synced BatchNorm sums, one NCCL all-reduce of the P-vector per HVP)" % world
+            "unit_note": "one HVP = Hv of one %d-image minibatch (weak scaling: every GPU holds its own minibatch shard "
+                         "of a global batch %d with synced BatchNorm; N GPUs complete N minibatch equivalents per step)"
+                         % (batch, batch * world),
+            "parallelism": "dp%d (minibatch sharded, synced BatchNorm sums, one all-reduce of the P-vector per HVP)" % world
             if world > 1 else "single GPU",
             "l2": "no flush: the HVP streams its value/tangent/adjoint caches, working set far above the 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _golden_for_bench(kind, batch):
+    """the reference's own outputs for the benched shape (tests/golden, generated by oracle/make_golden.py)"""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", kind + ".npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path, allow_pickle=False)
+    if "x" not in g or g["x"].shape[0] != batch:
+        return None
+    return g
+
+
+def per_config_table(args, skip):
+    """device-resident HVP/s of the other BASELINE configs on this GPU (same kernels, same loop)"""
+    import numpy as np
+    import torch
+    from optwboundeigenval_b200 import zoo
+    from optwboundeigenval_b200.hvp_operator import B200HVPOperator, clear_plans
+    rows = {}
+    for kind in ("forest", "usps", "chest_densenet121", "chest_vgg"):
+        if kind == skip:
+            continue
+        try:
+            model, loss = zoo.build(kind)
+            model.train()
+            batch = zoo.CONFIGS[kind][3]
+            x, y = zoo.synthetic_batch(kind, batch)
+            op = B200HVPOperator(model, [x, y], loss)
+            P = sum(p.numel() for p in model.parameters())
+            v0 = torch.from_numpy(np.ones(P) / np.sqrt(P)).cuda()
+            n = 200 if P < 100000 else 10
+            op.power_iterate(v0, 0.0, 3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = op.power_iterate(v0, 0.0, n)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            rows[kind] = {"hvp_per_s": 1e3 / ms, "ms_per_step": ms, "batch": batch, "P": P, "steps": n,
+                          "lambda": out.lam}
+            del op, model
+            clear_plans()
+            torch.cuda.empty_cache()
+        except Exception as e:   # noqa: BLE001
+            rows[kind] = {"error": repr(e)}
+    return rows
 
 
 def run_b200(args):
@@ -210,6 +398,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from optwboundeigenval_b200 import _lib, zoo
+    from optwboundeigenval_b200 import hvp_operator
     from optwboundeigenval_b200.hvp_operator import B200HVPOperator
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,16 +409,27 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
     kind = args.config
     batch = args.batch or zoo.CONFIGS[kind][3]
+    warmup = max(args.warmup, 3)
     model, loss = zoo.build(kind)            # same seed on every rank: replicated parameters
+    gold = _golden_for_bench(kind, batch)
+    if gold is not None:                     # the reference's own weights for this shape: parity is checked below
+        sd = model.state_dict()
+        j, new = 0, {}
+        for k, t in sd.items():
+            n = t.numel()
+            new[k] = torch.from_numpy(np.asarray(gold["state0"][j:j + n])).to(t.dtype).view(t.shape)
+            j += n
+        model.load_state_dict(new)
     model.train()
     x, y = zoo.synthetic_batch(kind, batch, seed=zoo.SEED + 1000 * rank)     # each rank its own shard
     op = B200HVPOperator(model, [x, y], loss)
+    op.async_host_vectors = True             # pinned host vectors are copied without a host-side wait (see its docstring)
     P = sum(p.numel() for p in model.parameters())
     v0 = torch.from_numpy(np.ones(P) / np.sqrt(P)).cuda()
-    op.Hv(v0, storedGrad=True)               # base pass + first HVP: plan, workspaces, graph capture
+    hv_first = op.Hv(v0, storedGrad=True)    # base pass + first HVP: plan, workspaces, graph capture
     torch.cuda.synchronize()
 
     def barrier():
@@ -237,8 +437,40 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity of the benched shape -------------------------------------------------------------------------
+    parity = {}
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+    if world == 1 and gold is not None and np.array_equal(gold["x"], x.numpy()):
+        parity = {"against": "tests/golden/%s.npz (unmodified reference, CPU fp32, batch %d)" % (kind, batch),
+                  "hv_rel_err": rel(hv_first.cpu().numpy(), gold["hv_v0"]),
+                  "grad_rel_err": rel(op.stored_grad.cpu().numpy(), gold["grad"]),
+                  "tolerance": 1e-4}
+    elif world > 1:
+        # sharded HVP (synced BatchNorm sums + all-reduce) against the single-GPU HVP of the concatenated batch
+        xs = [torch.empty_like(x).cuda() for _ in range(world)]
+        ys = [torch.empty_like(y).cuda() for _ in range(world)]
+        dist.all_gather(xs, x.cuda())
+        dist.all_gather(ys, y.cuda())
+        if rank == 0:
+            hvp_operator.set_data_parallel(False)
+            try:
+                one = B200HVPOperator(model, [torch.cat(xs), torch.cat(ys)], loss)
+                hv_one = one.Hv(v0, storedGrad=True)
+                parity = {"against": "single-GPU HVP of the concatenated %d-image batch" % (batch * world),
+                          "hv_rel_err": rel(hv_first.cpu().numpy(), hv_one.cpu().numpy()),
+                          "grad_rel_err": rel(op.stored_grad.cpu().numpy(), one.stored_grad.cpu().numpy()),
+                          "tolerance": 1e-4}
+                del one
+            finally:
+                hvp_operator._DATA_PARALLEL = True     # keep the sharded plan cached
+        barrier()
+
     # ---- device-resident loop -------------------------------------------------------------------
-    op.power_iterate(v0, 0.0, max(args.warmup, 3))
+    op.power_iterate(v0, 0.0, warmup)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -254,20 +486,26 @@ def run_b200(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert out.iters == args.steps - 1, "the timed loop must run exactly --steps iterations"
+    if gold is not None and parity and "rho1_traj" in gold and world == 1:
+        m = min(len(gold["rho1_traj"]), args.steps)
+        traj = op.power_iterate(v0, 0.0, m, want_trajectory=True).trajectory
+        parity["lambda_rel_err_first_iterations"] = float(np.max(np.abs(traj[:m, 1] - gold["rho1_traj"][:m, 1])
+                                                                 / np.abs(gold["rho1_traj"][:m, 1])))
+        parity["lambda_tolerance"] = 1e-3
 
     # ---- end to end through the reference-facing operator call, host vectors ----------------------
     v_host = torch.from_numpy(np.ones(P) / np.sqrt(P)).pin_memory()      # this step's input: pinned host memory
     r_host = torch.empty(P, dtype=torch.float64).pin_memory()            # this step's result, read back every step
     cur = torch.cuda.current_stream()
+    vh, rh = v_host.numpy(), r_host.numpy()
 
     def e2e_step():
-        r = op.Hv(v_host, storedGrad=True)          # 8P bytes host -> device inside the call
+        r = op.Hv(v_host, storedGrad=True)          # 8P bytes host -> device inside the call (async, pinned)
         r_host.copy_(r, non_blocking=True)          # 8P bytes device -> host
         cur.synchronize()
-        a = r_host.numpy()
-        np.divide(a, np.linalg.norm(a), out=v_host.numpy())             # next input depends on this output
+        np.multiply(rh, 1.0 / np.sqrt(np.dot(rh, rh)), out=vh)          # next input depends on this output
 
-    for _ in range(3):
+    for _ in range(warmup):
         e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,11 +519,10 @@ def run_b200(args):
     # ---- second headline metric: regularised steps/sec ---------------------------------------------
     # one step = the minibatch body of iter() (opt.py:608-699): host batch -> device, new operator, base pass,
     # k = 20 power iterations (max_pow_iter = 20, pow_iter_eps = 0: pinned, as SURVEY 8d prescribes), penalty
-    # gradient vGHv (K = 0 so the penalty is always active), fused step assembly, SGD update.
+    # gradient vGHv (K = 0 so the penalty is always active), fused step assembly + update.
     reg = None
     if not args.no_reg:
         try:
-            import contextlib
             from optwboundeigenval_b200.spectral import SpectralState
             st = SpectralState(model, loss, mu=0.01, K=0.0, pow_iter_eps=0.0, max_pow_iter=20, ignore_bad_vals=False)
             opt_sgd = torch.optim.SGD(model.parameters(), lr=1e-4)
@@ -310,7 +547,7 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(tr, op=dist.ReduceOp.MAX)
             ms_reg = float(tr[0])
-            reg = {"value": world * 1e3 / ms_reg, "unit": "regularized steps/s (32-image minibatches)", "ms_per_step": ms_reg,
+            reg = {"value": world * 1e3 / ms_reg, "unit": "regularized steps/s", "ms_per_step": ms_reg,
                    "steps": n_reg, "hvp_per_step": 20, "penalty": "mu=0.01, K=0 (active every step): base pass + 20 HVPs + vGHv + "
                    "fused step assembly + SGD update; batch copied from pinned host memory every step",
                    "h2d_bytes_per_step": int(x.numel() * 4 + y.numel() * 8), "rho": float(st.rho)}
@@ -325,7 +562,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel of the HVP pass (CUDA events around every launch, on the plan's stream) ----
     # conv_fwd and conv_dgrad are template instances of ONE kernel (conv_tma_kernel): they are one row here.
     peaks = _peaks()
-    # every rank runs the profiled pass (it contains the pass's NCCL all-reduces); rank 0 reports
+    # every rank runs the profiled pass (it contains the pass's collectives); rank 0 reports
     prof = op.plan.profile(1, reps=3)
     line = None
     if rank == 0:
@@ -338,49 +575,78 @@ def run_b200(args):
         top = max(fam.values(), key=lambda r: r["ms"])
         tot_ms = sum(r["ms"] for r in prof)
         is_gemm = top["name"].startswith("conv")
-        tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 = half the dense bf16 rate on B200 (1.1 vs 2.25 PFLOP/s)
+        try:
+            tf32_peak, tf32_src = measure_tf32_peak(), "measured in this run: torch.matmul 8192^3 with allow_tf32, best of 10"
+        except Exception as e:   # noqa: BLE001
+            tf32_peak, tf32_src = peaks["bf16_tflops"] / 2.0, "fallback bf16/2 (%r)" % (e,)
         ai = top["flops"] / max(top["bytes"], 1.0)         # algorithmic FLOP per algorithmic byte
         balance = tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
         gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         tfl = top["flops"] / (top["ms"] * 1e-3) / 1e12
         if is_gemm and ai >= balance:
-            roof = {"bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": tfl / peaks["bf16_tflops"], "traffic": None}
+            roof = {"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": tfl / tf32_peak, "traffic": None}
         else:
             roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "traffic": None}
-        ncu = _ncu_summary()
+        ncu, ncu_path = _ncu_summary()
         if ncu and top["name"] in ncu:                # dram__bytes_read + dram__bytes_write per launch, ncu --set full capture
             roof["traffic"] = ncu[top["name"]].get("dram_bytes_per_launch")
-            roof["traffic_source"] = "profiles/r1_ncu_top_kernel.json: " + ncu[top["name"]].get("capture", "")
+            roof["traffic_source"] = ncu_path + ": " + ncu[top["name"]].get("capture", "")
         roof.update({"kernel": top["name"], "launches_per_step": top["launches"],
                      "ms_per_step_in_kernel": top["ms"], "share_of_step_kernel_time": top["ms"] / tot_ms,
                      "algorithmic_bytes_per_step": top["bytes"], "algorithmic_flops_per_step": top["flops"],
                      "arithmetic_intensity_flop_per_byte": ai, "machine_balance_flop_per_byte_tf32": balance,
-                     "tensor_side": {"achieved_tflops": tfl, "peak_bf16_tflops": peaks["bf16_tflops"],
-                                     "frac_of_bf16_peak": tfl / peaks["bf16_tflops"],
+                     "tensor_side": {"achieved_tflops": tfl, "peak_tf32_tflops": tf32_peak, "peak_source": tf32_src,
+                                     "frac_of_tf32_peak": tfl / tf32_peak,
                                      "note": "3xTF32 emulation passes are not counted as algorithmic FLOPs"},
-                     "peak_source": peaks["source"] + " (MEASURED_PEAKS.json burst copy bandwidth / bf16 matmul)",
+                     "peak_source": peaks["source"] + " (MEASURED_PEAKS.json burst copy bandwidth)",
                      "note": "thin layers (12..48 output channels): algorithmic intensity below the TF32 machine balance, "
                              "so the HBM roofline bounds the kernel; event time includes ~2 us of launch gap per launch"})
-        cpu = None
+        cpu = cpu_reg = yard = None
         if world == 1 and not args.no_cpu:
-            rate, n, dt = cpu_hvp_rate(kind, batch)
-            cpu = {"value": rate, "unit": "HVP/s", "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": "%d Hv calls of the same %d-image minibatch in %.1f s (oracle/autograd_oracle.py)" % (n, batch, dt)}
+            try:
+                n_cpu = 12 if kind in ("cifar_densenet", "usps", "forest") else 2
+                rate, dt, how = reference_comp_rho_rate(kind, batch, 2, n_cpu)
+                cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": how,
+                       "sample": "%d iterations of comp_rho's loop on the same %d-image minibatch in %.1f s after 2 warm-up "
+                                 "iterations (%s)" % (n_cpu, batch, dt, "unmodified reference from baseline/_ref"
+                                                      if how == "reference" else "oracle/autograd_oracle.py")}
+            except Exception as e:   # noqa: BLE001
+                cpu = {"error": repr(e)}
+            if reg is not None and "error" not in reg and kind in ("cifar_densenet", "usps", "forest"):
+                try:
+                    cpu_reg = reference_iter_body_rate(kind, batch)
+                except Exception as e:   # noqa: BLE001
+                    cpu_reg = {"error": repr(e)}
+            if not args.no_yardstick:
+                # the reference's own autograd path on THIS GPU (its use_gpu=True branch: cuBLAS / cuDNN double backward,
+                # torch defaults: cudnn.allow_tf32 = True, cuda.matmul.allow_tf32 = False) -- context, not the target
+                try:
+                    rate, dt = reference_gpu_hv_rate(kind, batch, 3, 10)
+                    yard = {"value": rate, "unit": UNIT, "kind": "reference", "device": torch.cuda.get_device_name(),
+                            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                            "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+                            "sample": "10 Hv(v, storedGrad=True) calls of the unmodified opt.HVPOperator(use_gpu=True) after 3 warm-up calls"}
+                except Exception as e:   # noqa: BLE001
+                    yard = {"error": repr(e)[:300]}
         vec = None
         if world == 1 and not args.no_vec:
             try:
                 vec = vector_roofline(peaks)
             except Exception as e:   # noqa: BLE001
                 vec = {"error": str(e)}
+        table = None
+        if world == 1 and not args.no_table:
+            table = per_config_table(args, kind)
+        if reg is not None and cpu_reg is not None:
+            reg["cpu_reference"] = cpu_reg
         value = world * args.steps / (ms * 1e-3)
-        line = {"metric": "HVPs/sec (power-iter lambda_max)", "value": value,
-                "unit": "HVP/s (32-image minibatch equivalents)" if kind == "cifar_densenet" else "HVP/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        line = {"metric": METRIC, "value": value, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": _config(kind, batch, world),
-                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "HVP/s",
+                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * P},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
@@ -388,6 +654,9 @@ def run_b200(args):
                 "roofline_vector_kernels": vec,
                 "regularized_step": reg,
                 "cpu_baseline": cpu,
+                "gpu_autograd_yardstick": yard,
+                "per_config": table,
+                "parity": parity or None,
                 "kernel_profile_ms": {r["name"]: round(r["ms"], 4) for r in prof},
                 "lambda_max": out.lam}
         sys.stdout.flush()
@@ -400,18 +669,20 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cifar_densenet")
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-vec", action="store_true", help="skip the vector-kernel HBM roofline leg")
     ap.add_argument("--no-reg", action="store_true", help="skip the regularised-step leg")
+    ap.add_argument("--no-yardstick", action="store_true", help="skip the reference-on-GPU (stock autograd) leg")
+    ap.add_argument("--no-table", action="store_true", help="skip the per-config table")
     args = ap.parse_args()
+    if args.steps < 1 or args.warmup < 0:
+        raise SystemExit("bench.py: --steps must be >= 1 and --warmup >= 0")
     if args.impl == "reference":
-        args.steps = min(args.steps, 12)
-        args.warmup = min(args.warmup, 2)
         run_reference(args)
     else:
         run_b200(args)

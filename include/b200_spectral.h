@@ -132,6 +132,12 @@ int b2s_base_pass(b2s_plan* p, const float* d_params, const float* d_x, const vo
 /* H*v = HVPOperator.Hv(vec, storedGrad=True) (opt.py:77-108). d_v fp64 [n_params]
  * (rounded to fp32 as the reference's cast does), d_out fp64 [n_params]. Asynchronous. */
 int b2s_hv(b2s_plan* p, const double* d_v, double* d_out);
+/* comp_f (opt.py:544-572) and, through it, every forward pass of test_model (opt.py:954): forward only, BatchNorm in
+ * evaluation mode (running statistics read, not updated), loss of the head into d_loss_out (fp64 [1]) and the raw
+ * logits [batch, classes] into d_logits_out (optional; a softmax / sigmoid tail of the model is the caller's).
+ * Arguments as b2s_base_pass.  Local to the calling rank (no collective); forgets the cached base pass. */
+int b2s_eval_pass(b2s_plan* p, const float* d_params, const float* d_x, const void* d_y, const float* d_coef,
+                  int32_t batch, double loss_scale, float* d_logits_out, double* d_loss_out);
 /* grad_w (v^T H v) = HVPOperator.vGHv (opt.py:110-152). Asynchronous. */
 int b2s_vghv(b2s_plan* p, const double* d_v, double* d_out);
 /* fp32 results of the last passes, device pointers owned by the plan (float [n_params]) */
@@ -228,10 +234,35 @@ int b2s_kfac_apply(b2s_plan* p, const double* d_r, double* d_out);
 int b2s_step_assemble(const double* d_gradf, const double* d_gradrho, double coef, int64_t n, double* d_p, float* d_p32,
                       void* stream);
 
+/* The remainder of iter()'s minibatch body fused on flat vectors (opt.py:535-542 clip, 616-659 assembly, 696-699
+ * optimizer step).  b2s_clip_norm: d_out2 = {|x|, clip > 0 && |x| > clip ? clip / |x| : 1} without a host sync
+ * (d_scratch: b2s_clip_scratch_doubles() doubles, zeroed once by the caller).  b2s_step_fused over n elements:
+ *   p = grad f + coef * s * grad rho          (s = d_scale2[1] when given; grad rho itself is rescaled in place when
+ *                                              write_gradrho, as the reference's `self.gradrho *= clip / grn`)
+ *   d_p (fp64, optional), d_p32 = (float)p    (param.grad)
+ *   kind 1: torch.optim.SGD update, kind 2: torch.optim.Adam update of d_params with state vectors d_state1
+ *   (momentum buffer / exp_avg) and d_state2 (exp_avg_sq), fp32 arithmetic in torch's operation order. */
+typedef struct {
+    int32_t kind;            /* 0 assemble only, 1 SGD, 2 Adam */
+    int32_t first_step;      /* SGD: this step initialises the momentum buffer (buf = grad) */
+    int32_t nesterov, maximize, write_gradrho;
+    double lr, momentum, dampening, weight_decay;
+    double beta1, beta2, eps;
+    double step_size;        /* Adam: lr / (1 - beta1^t) */
+    double bias2_sqrt;       /* Adam: sqrt(1 - beta2^t) */
+} b2s_step_opt;
+int b2s_clip_norm(const double* d_x, int64_t n, double clip, double* d_scratch, double* d_out2, void* stream);
+int b2s_clip_scratch_doubles(void);
+int b2s_step_fused(const double* d_gradf, double* d_gradrho, double coef, const double* d_scale2, int64_t n, double* d_p,
+                   float* d_p32, float* d_params, float* d_state1, float* d_state2, const b2s_step_opt* opt, void* stream);
+
 /* ---- data parallelism (one process per GPU) ------------------------------------------- */
 int b2s_comm_unique_id(void* h_id128);                       /* 128 bytes, rank 0 */
 int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world);
 int b2s_comm_destroy(b2s_plan* p);
+/* Ragged shards: the number of samples over ALL ranks of the next base pass (0 = batch x world).  The loss scale
+ * handed to b2s_base_pass must be 1 / global_batch; BatchNorm statistics and the K-FAC factors divide by it. */
+int b2s_plan_set_global_batch(b2s_plan* p, int64_t global_batch);
 /* One-shot all-reduce of the small per-layer BatchNorm sums over NVLink peer memory instead of NCCL (the reference
  * has no counterpart: it is single-device).  After b2s_comm_init every rank calls
  * b2s_comm_peer_local (allocates its exchange buffer, returns the 64-byte cudaIpcMemHandle), the handles are

@@ -30,6 +30,13 @@ class ProfEntry(ctypes.Structure):
                 ("bytes", c_double)]
 
 
+class StepOpt(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("first_step", c_int32), ("nesterov", c_int32), ("maximize", c_int32),
+                ("write_gradrho", c_int32), ("lr", c_double), ("momentum", c_double), ("dampening", c_double),
+                ("weight_decay", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+                ("step_size", c_double), ("bias2_sqrt", c_double)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "b2s_abi_version": (c_int32, []),
@@ -47,6 +54,8 @@ SIGNATURES = {
     "b2s_base_pass": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_void_p,
                                 c_void_p]),
     "b2s_hv": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "b2s_eval_pass": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_void_p,
+                                c_void_p]),
     "b2s_vghv": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_debug_read": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b2s_profile_pass": (c_int32, [c_void_p, c_int32, c_int32, POINTER(ProfEntry), c_int32, POINTER(c_int32)]),
@@ -68,9 +77,14 @@ SIGNATURES = {
     "b2s_kfac_set": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
     "b2s_kfac_apply": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b2s_step_assemble": (c_int32, [c_void_p, c_void_p, ctypes.c_double, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b2s_clip_norm": (c_int32, [c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    "b2s_clip_scratch_doubles": (c_int32, []),
+    "b2s_step_fused": (c_int32, [c_void_p, c_void_p, c_double, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, POINTER(StepOpt), c_void_p]),
     "b2s_comm_unique_id": (c_int32, [c_void_p]),
     "b2s_comm_init": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
     "b2s_comm_destroy": (c_int32, [c_void_p]),
+    "b2s_plan_set_global_batch": (c_int32, [c_void_p, c_int64]),
     "b2s_comm_peer_local": (c_int32, [c_void_p, c_void_p]),
     "b2s_comm_peer_attach": (c_int32, [c_void_p, c_void_p]),
     "b2s_comm_peer_ready": (c_int32, [c_void_p]),

@@ -16,6 +16,7 @@
 
 #include "kernels.h"
 #include "peer.cuh"
+#include <algorithm>
 
 namespace b2s {
 
@@ -612,6 +613,32 @@ __global__ void __launch_bounds__(256) bn_corr_apply_kernel(const BnArgs a, cons
 }
 
 int bn_corr_sums() { return kCorrSums; }
+
+// ---- evaluation mode (comp_f / test_model forward passes, opt.py:544-572, 912-1039) -------------------------
+// y = gamma * (x - running_mean) / sqrt(running_var + eps) + beta, ReLU fused; the running statistics are read,
+// never written.  One thread per element of a (sample, channel) plane slice; 8 B of traffic per element.
+__global__ void __launch_bounds__(256) bn_eval_kernel(const BnArgs a) {
+    const int c = blockIdx.y, n = blockIdx.z;
+    const float inv = rsqrtf(a.running_var[c] + a.eps);
+    const float sc = a.gamma[c] * inv, sh = a.beta[c] - a.running_mean[c] * sc;
+    const float* __restrict__ x = a.x[0] + (long long)n * a.in_sstride + (long long)c * a.HW;
+    float* __restrict__ y = a.yk + (long long)n * a.out_sstride + (long long)c * a.HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.HW; i += gridDim.x * blockDim.x) {
+        float v = fmaf(x[i], sc, sh);
+        if (a.relu) v = fmaxf(v, 0.f);
+        y[i] = v;
+    }
+}
+
+int launch_bn_eval(cudaStream_t st, const BnArgs& a) {
+    if (!a.running_mean || !a.running_var) { set_error("BatchNorm evaluation pass: running statistics are not bound"); return -1; }
+    const double elems = (double)a.batch * a.C * a.HW;
+    ProfScope prof("bn_eval", 2.0 * elems, 8.0 * elems, st);
+    dim3 grid((unsigned)std::min(cdiv(a.HW, 256), 64), (unsigned)a.C, (unsigned)a.batch);
+    bn_eval_kernel<<<grid, 256, 0, st>>>(a);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_bn_corr_stats(cudaStream_t st, const BnArgs& a, const float* gc) {
     ProfScope prof("bn_corr_stats", 20.0 * a.batch * a.C * a.HW, 4.0 * 6 * (double)a.batch * a.C * a.HW, st);

@@ -60,6 +60,7 @@ struct Comm {
     void* peer_base[kPeerMax] = {};
     unsigned long long* d_seq = nullptr;
     unsigned int* d_ticket = nullptr;
+    int* h_error = nullptr;            // mapped pinned host memory (peer.cuh: a peer did not arrive in time)
     bool peers_ready = false;
     PeerCtx ctx = {};
     PeerCtx* d_ctx = nullptr;          // device copy for kernels that do the exchange themselves (bn.cu)
@@ -107,6 +108,7 @@ int comm_destroy(Comm* c) {
     if (c->xbuf) cudaFree(c->xbuf);
     if (c->d_seq) cudaFree(c->d_seq);
     if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->h_error) cudaFreeHost(c->h_error);
     if (c->d_ctx) cudaFree(c->d_ctx);
     NcclApi* a = nccl();
     if (a && c->comm) a->CommDestroy(c->comm);
@@ -136,6 +138,8 @@ int comm_peer_local(Comm* c, void* h_handle64) {
         B2S_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
         B2S_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
         B2S_CUDA(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+        B2S_CUDA(cudaHostAlloc(&c->h_error, sizeof(int), cudaHostAllocMapped));
+        *c->h_error = 0;
         B2S_CUDA(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
@@ -170,6 +174,14 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
     x.own_data = reinterpret_cast<double*>(static_cast<char*>(c->xbuf) + kPeerFlagBytes);
     x.seq = c->d_seq;
     x.ticket = c->d_ticket;
+    {
+        int* dev_err = nullptr;
+        B2S_CUDA(cudaHostGetDevicePointer(&dev_err, c->h_error, 0));
+        x.error = dev_err;
+        const char* e = getenv("B2S_PEER_TIMEOUT_S");
+        const double secs = e ? atof(e) : 600.0;
+        x.timeout_ns = (unsigned long long)((secs > 0 ? secs : 600.0) * 1e9);
+    }
     x.rank = c->rank; x.world = c->world;
     if (!c->d_ctx) B2S_CUDA(cudaMalloc(&c->d_ctx, sizeof(PeerCtx)));
     B2S_CUDA(cudaMemcpy(c->d_ctx, &x, sizeof(PeerCtx), cudaMemcpyHostToDevice));
@@ -179,6 +191,12 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
 }
 
 int comm_peer_ready(const Comm* c) { return (c && c->peers_ready) ? 1 : 0; }
+int comm_peer_error(Comm* c) {
+    if (!c || !c->h_error) return 0;
+    const int e = *((volatile int*)c->h_error);
+    if (e) *c->h_error = 0;
+    return e;
+}
 void comm_peer_disable(Comm* c) { if (c) c->peers_ready = false; }
 
 const PeerCtx* comm_peer_ctx(Comm* c) {

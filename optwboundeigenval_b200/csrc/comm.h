@@ -25,6 +25,8 @@ int comm_peer_attach(Comm* c, const void* h_handles);           // world x 64 by
 // all-reduces the flags and disables the path everywhere when one rank could not attach)
 int comm_peer_ready(const Comm* c);
 void comm_peer_disable(Comm* c);
+// 0, or 1 + the rank of a peer that did not reach an exchange within B2S_PEER_TIMEOUT_S (reading clears it)
+int comm_peer_error(Comm* c);
 struct PeerCtx;
 // device-resident exchange context for kernels that do the exchange themselves (peer.cuh), NULL when unavailable
 const PeerCtx* comm_peer_ctx(Comm* c);

@@ -9,14 +9,17 @@
 //                 CrossEntropyLoss applies log-softmax AGAIN
 //   WBCE          dcnn.py:375-400 on raw logits (MyVggNet16_bn)
 //   SIGMOID_WBCE  dcnn.py:275: Linear -> Sigmoid, then BCE-with-logits applies a sigmoid again
-// One thread per sample; the class dimension (<= 64) lives in thread-local arrays, arithmetic
-// in fp64 (inputs and outputs fp32).
+// One thread per sample, arithmetic in fp64 (inputs and outputs fp32).  Up to 64 classes the class
+// dimension lives in thread-local arrays; wider heads (CIFAR-100: cifar100_ResNet_mu0.py) run one
+// single-thread block per sample with the jets in shared memory (B x C is tiny either way).  A label outside [0, C) poisons the sample's loss and
+// adjoint with NaN instead of reading out of bounds.
 #include "kernels.h"
 #include "../../include/b200_spectral.h"
 
 namespace b2s {
 
-constexpr int kMaxClasses = 64;
+constexpr int kLocalClasses = 64;
+constexpr int kMaxClasses = 640;       // 3 jets x 3 doubles x 640 classes = 46 KB of shared memory
 
 template <int K>
 using JD = Jet<K, double>;
@@ -50,12 +53,19 @@ __device__ inline double bce_with_logits(double u, double t) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= a.batch) return;
+__device__ inline void head_sample(const HeadArgs& a, const int n, JD<K>* z, JD<K>* p, JD<K>* q) {
     const int C = a.C;
-    JD<K> z[kMaxClasses];
+    if (a.kind == B2S_HEAD_CE || a.kind == B2S_HEAD_SOFTMAX_CE) {
+        const long long y = a.labels[n];
+        if (y < 0 || y >= C) {                       // invalid label: visible, not out of bounds
+            float* bad = a.zbar + (long long)n * a.zs;
+            for (int i = 0; i < C; ++i) bad[i] = __int_as_float(0x7fc00000);
+            if (K == 0 && a.loss) atomicAdd(a.loss, (double)__int_as_float(0x7fc00000));
+            return;
+        }
+    }
     for (int i = 0; i < C; ++i) {
+        z[i] = JD<K>();
         const long long idx = (long long)n * a.zs + i;
         z[i].c[0] = a.z[0][idx];
         if (K >= 1) z[i].c[1] = a.z[1][idx];
@@ -64,7 +74,6 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
     float* out = a.zbar + (long long)n * a.zs;
     double loss = 0.0;
     if (a.kind == B2S_HEAD_CE) {
-        JD<K> p[kMaxClasses];
         double lse;
         softmax_jet<K>(z, p, C, &lse);
         const int y = (int)a.labels[n];
@@ -75,7 +84,6 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
         }
         loss = -(z[y].c[0] - lse) * a.loss_scale;
     } else if (a.kind == B2S_HEAD_SOFTMAX_CE) {
-        JD<K> p[kMaxClasses], q[kMaxClasses];
         softmax_jet<K>(z, p, C, nullptr);
         double lse;
         softmax_jet<K>(p, q, C, &lse);
@@ -116,6 +124,21 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
     if (K == 0 && a.loss) atomicAdd(a.loss, loss);
 }
 
+template <int K>
+__global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.batch) return;
+    JD<K> z[kLocalClasses], p[kLocalClasses], q[kLocalClasses];
+    head_sample<K>(a, n, z, p, q);
+}
+
+template <int K>
+__global__ void __launch_bounds__(32) head_wide_kernel(const HeadArgs a) {
+    extern __shared__ double head_smem[];
+    JD<K>* z = reinterpret_cast<JD<K>*>(head_smem);
+    if (threadIdx.x == 0) head_sample<K>(a, blockIdx.x, z, z + a.C, z + 2 * a.C);
+}
+
 int launch_head(cudaStream_t st, int order, const HeadArgs& a) {
     if (a.C > kMaxClasses) {
         set_error("loss head supports at most %d classes, got %d", kMaxClasses, a.C);
@@ -123,9 +146,16 @@ int launch_head(cudaStream_t st, int order, const HeadArgs& a) {
     }
     ProfScope prof("loss_head", 0.0, 4.0 * a.batch * a.C * (order + 2), st);
     const int blocks = cdiv(a.batch, 128);
-    if (order == 0) head_kernel<0><<<blocks, 128, 0, st>>>(a);
-    else if (order == 1) head_kernel<1><<<blocks, 128, 0, st>>>(a);
-    else head_kernel<2><<<blocks, 128, 0, st>>>(a);
+    if (a.C <= kLocalClasses) {
+        if (order == 0) head_kernel<0><<<blocks, 128, 0, st>>>(a);
+        else if (order == 1) head_kernel<1><<<blocks, 128, 0, st>>>(a);
+        else head_kernel<2><<<blocks, 128, 0, st>>>(a);
+    } else {
+        const size_t sm = (size_t)3 * a.C * sizeof(JD<0>);
+        if (order == 0) head_wide_kernel<0><<<a.batch, 32, sm, st>>>(a);
+        else if (order == 1) head_wide_kernel<1><<<a.batch, 32, sm, st>>>(a);
+        else head_wide_kernel<2><<<a.batch, 32, sm, st>>>(a);
+    }
     B2S_LAUNCH_CHECK();
     return 0;
 }

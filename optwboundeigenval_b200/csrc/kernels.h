@@ -87,6 +87,7 @@ int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_bwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_bwd_apply(cudaStream_t st, int order, const BnArgs& a);
+int launch_bn_eval(cudaStream_t st, const BnArgs& a);     // evaluation mode: running statistics, no update
 // fused statistics+apply (cooperative launch); return 1 = not applicable, use the two-kernel form
 int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stats);
 int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a);

@@ -4,6 +4,7 @@
 // have mapped with cudaIpc (comm.cu).  peer_exchange_block() is executed by ONE thread block per rank:
 // publish the vector in slot (call number & 1), raise the flag (st.release.sys), poll the peers' flags
 // (ld.acquire.sys through NVSwitch), add the peers' vectors in rank order (bitwise identical on all ranks).
+// A peer that does not arrive within B2S_PEER_TIMEOUT_S seconds (default 600) sets a host-visible error flag.
 // A rank can be at most one call ahead of a peer -- it needs the peer's flag of the previous call to get
 // there -- so two slots are enough and no slot is overwritten while a peer still reads it.
 // The BatchNorm kernels call it between their statistics and apply phases (bn.cu), which makes the per-layer
@@ -25,8 +26,16 @@ struct PeerCtx {
     unsigned long long* own_flag;
     unsigned long long* seq;           // device-resident call counter (graph replays advance it)
     unsigned int* ticket;              // arrival counter of the kernel whose last block performs the exchange
+    int* error;                        // mapped host memory: set to 1 + peer rank when a peer did not arrive in time
+    unsigned long long timeout_ns;     // B2S_PEER_TIMEOUT_S (default 600 s), measured with %globaltimer
     int rank, world;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
@@ -49,9 +58,18 @@ __device__ __forceinline__ void peer_exchange_block(double* buf, const int n, co
     if (tid == 0) st_release_sys(ctx.own_flag + slot * 16, seq);
     if (tid < ctx.world && tid != ctx.rank) {
         const unsigned long long* f = ctx.flag[tid] + slot * 16;
-        const long long t0 = clock64();
+        // a peer that is merely late (graph instantiation, lazy module load, a stalled data loader) is waited for;
+        // one that never arrives within the (wall-clock, configurable) limit raises the host-visible error flag and
+        // the exchange returns with an incomplete sum -- the host reports it at the end of the call (plan.cu leave()),
+        // the context stays usable (no trap)
+        unsigned long long t0 = 0;
+        unsigned int spins = 0;
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > 8000000000LL) { asm volatile("trap;"); }      // a lost peer becomes an error, not a hang
+            if ((++spins & 0xfffu) == 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > ctx.timeout_ns) { *((volatile int*)ctx.error) = 1 + tid; break; }
+            }
         }
     }
     __syncthreads();

@@ -106,6 +106,8 @@ struct b2s_pistate {
 struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long kernels = 0;
+    double loss_scale = 0.0;          // baked into the captured head kernels
+    long long global_batch = 0;       // baked into the captured BatchNorm kernels
 };
 
 struct b2s_plan {
@@ -188,6 +190,21 @@ struct b2s_plan {
     b2s_pistate* pi = nullptr;
     Comm* comm = nullptr;
     int world = 1;
+    long long global_batch = 0;       // samples over all ranks of the cached base pass (0: batch * world)
+
+    // eigen-iteration loop control (b2s_power_iterate)
+    int* h_done = nullptr;            // pinned ring of `done` flags read back with a lag
+    static constexpr int kMaxLag = 8;
+    cudaEvent_t ev_poll[kMaxLag + 1] = {};
+    int poll_lag = -1;                // -1: not measured yet
+    struct LoopGraph {                // whole loop as ONE graph launch: WHILE node around (HVP pass + vector kernels)
+        cudaGraphExec_t exec = nullptr;
+        long long kernels_per_iter = 0;
+        double loss_scale = 0.0;
+        long long global_batch = 0;
+    };
+    std::map<long long, LoopGraph> loops;   // key = batch
+    int device_loop = -1;             // -1 undecided, 0 unavailable / disabled, 1 in use
 };
 
 namespace b2s {
@@ -257,7 +274,7 @@ static BnArgs bn_args(b2s_plan* p, int oi, int K) {
     a.eps = op.eps; a.momentum = op.momentum;
     a.relu = (op.flags & B2S_F_RELU) ? 1 : 0;
     a.first = first ? 1 : 0;
-    a.count = (long long)p->batch * p->world * a.HW;
+    a.count = (p->global_batch > 0 ? p->global_batch : (long long)p->batch * p->world) * a.HW;
     a.accumulate = (op.flags & B2S_F_BWD_ACC) ? 1 : 0;
     a.pgrad_scale = 1.0f / (float)p->world;
     a.peer = (p->comm && 2 * a.C <= 4096) ? comm_peer_ctx(p->comm) : nullptr;
@@ -273,7 +290,7 @@ static inline const float* tc_image(const b2s_plan* p, int oi, int mode, const f
 }
 
 // ---- forward sweep of order K -----------------------------------------------------------------
-static int forward(b2s_plan* p, int K) {
+static int forward(b2s_plan* p, int K, bool eval_mode = false) {
     cudaStream_t st = p->stream;
     if (p->tc_njobs > 0 && get_tc_mode() != 0) {
         if (K == 0) B2S_TRY(launch_tc_pack(st, p->tc_jobs, p->tc_njobs, p->tc_total, p->params, p->tc_packW));
@@ -318,6 +335,10 @@ static int forward(b2s_plan* p, int K) {
         }
         case B2S_OP_BN: {
             const BnArgs a = bn_args(p, (int)oi, K);
+            if (eval_mode) {
+                B2S_TRY(launch_bn_eval(st, a));
+                break;
+            }
             const int do_stats = !(first && K > 0);
             int rc = 1;
             if ((!p->comm || a.peer) && p->bn_fused) rc = launch_bn_fwd_fused(st, K, a, do_stats);
@@ -560,6 +581,13 @@ static int backward_correction(b2s_plan* p) {
 
 static int run_pass_eager(b2s_plan* p, int K) {
     if (K == 3) return backward_correction(p);
+    if (K == 4) {                      // evaluation pass: local to the rank, no collective
+        Comm* comm = p->comm;
+        p->comm = nullptr;
+        const int rc = forward(p, 0, true);
+        p->comm = comm;
+        return rc;
+    }
     B2S_TRY(forward(p, K));
     B2S_TRY(backward(p, K));
     return 0;
@@ -569,8 +597,14 @@ static int run_pass_eager(b2s_plan* p, int K) {
 static int run_pass(b2s_plan* p, int K) {
     if (K < 3) B2S_TRY(alloc_order(p, K));
     if (!p->use_graphs) return run_pass_eager(p, K);
+    // (K = 3: compatibility sweep, K = 4: evaluation pass -- both live in the order-2 / order-0 arenas)
     const long long key = ((long long)K << 32) | (unsigned)p->batch;
     auto it = p->graphs.find(key);
+    if (it != p->graphs.end() && (it->second.loss_scale != p->loss_scale || it->second.global_batch != p->global_batch)) {
+        if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+        p->graphs.erase(it);
+        it = p->graphs.end();
+    }
     if (it == p->graphs.end()) {
         cudaGraph_t graph = nullptr;
         g_counting_paused = true;
@@ -594,6 +628,8 @@ static int run_pass(b2s_plan* p, int K) {
         }
         GraphEntry ge;
         ge.kernels = g_capture_count;
+        ge.loss_scale = p->loss_scale;
+        ge.global_batch = p->global_batch;
         e = cudaGraphInstantiate(&ge.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) {
@@ -608,8 +644,25 @@ static int run_pass(b2s_plan* p, int K) {
 }
 
 // order the plan stream after the caller's stream / the caller's stream after the plan stream
+static int peer_status(b2s_plan* p) {
+    if (!p->comm) return 0;
+    const int e = comm_peer_error(p->comm);
+    if (e) {
+        set_error("data-parallel exchange: rank %d did not reach a BatchNorm statistics exchange within B2S_PEER_TIMEOUT_S; "
+                  "the results of the last call are incomplete", e - 1);
+        return -9;
+    }
+    return 0;
+}
+static void drop_graphs(b2s_plan* p) {
+    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
+    for (auto& kv : p->loops) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    p->loops.clear();
+}
 static int enter(b2s_plan* p) {
     B2S_CUDA(cudaSetDevice(p->device));
+    B2S_TRY(peer_status(p));
     B2S_CUDA(cudaEventRecord(p->ev_in, p->caller));
     B2S_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in, 0));
     return 0;
@@ -617,7 +670,7 @@ static int enter(b2s_plan* p) {
 static int leave(b2s_plan* p) {
     B2S_CUDA(cudaEventRecord(p->ev_out, p->stream));
     B2S_CUDA(cudaStreamWaitEvent(p->caller, p->ev_out, 0));
-    return 0;
+    return peer_status(p);
 }
 
 static int pi_upload(b2s_pistate* s, cudaStream_t st) {
@@ -846,8 +899,9 @@ int b2s_plan_destroy(b2s_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    for (auto& kv : p->graphs)
-        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    drop_graphs(p);
+    if (p->h_done) cudaFreeHost(p->h_done);
+    for (auto& e : p->ev_poll) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 3; ++k) {
         cudaFree(p->fw[k]); cudaFree(p->bw[k]); cudaFree(p->out32[k]);
         cudaFree(p->fsum[k]); cudaFree(p->bsum[k]);
@@ -903,7 +957,7 @@ int b2s_plan_set_bn_buffers(b2s_plan* p, int32_t slot, void* rm, void* rv) {
     if (p->bn_rm[slot] != rm || p->bn_rv[slot] != rv) {
         // captured order-0 graphs hold the old pointers
         for (auto it = p->graphs.begin(); it != p->graphs.end();) {
-            if ((it->first >> 32) == 0) {
+            if ((it->first >> 32) == 0 || (it->first >> 32) == 4) {
                 if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
                 it = p->graphs.erase(it);
             } else {
@@ -927,10 +981,6 @@ int b2s_base_pass(b2s_plan* p, const float* d_params, const float* d_x, const vo
     if (wbce && !d_coef) { set_error("b2s_base_pass: weighted-BCE head needs d_coef"); return -1; }
     B2S_TRY(enter(p));
     cudaStream_t st = p->stream;
-    if (p->loss_scale != loss_scale) {          // baked into captured head kernels
-        for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-        p->graphs.clear();
-    }
     p->batch = batch;
     p->loss_scale = loss_scale;
     p->v_is_current = false;
@@ -964,6 +1014,47 @@ int b2s_hv(b2s_plan* p, const double* d_v, double* d_out) {
     B2S_TRY(enter(p));
     B2S_TRY(hv_impl(p, d_v));
     B2S_TRY(launch_cast_f32_f64(p->stream, p->out32[1], d_out, p->P, 1.0));
+    return leave(p);
+}
+
+// Forward-only evaluation pass (comp_f, opt.py:544-572; every forward of test_model goes through it, opt.py:954):
+// values of order 0 with BatchNorm in evaluation mode and the loss of the head.  It overwrites the value caches of
+// the base pass, so the plan forgets its cached minibatch (a later b2s_hv needs a new b2s_base_pass).
+int b2s_eval_pass(b2s_plan* p, const float* d_params, const float* d_x, const void* d_y, const float* d_coef, int32_t batch,
+                  double loss_scale, float* d_logits_out, double* d_loss_out) {
+    if (!p || !d_params || !d_x || !d_y) { set_error("b2s_eval_pass: null argument"); return -1; }
+    if (batch <= 0 || batch > p->max_batch) {
+        set_error("b2s_eval_pass: batch %d outside (0, %d]", batch, p->max_batch);
+        return -1;
+    }
+    const bool wbce = p->head == B2S_HEAD_WBCE || p->head == B2S_HEAD_SIGMOID_WBCE;
+    if (wbce && !d_coef) { set_error("b2s_eval_pass: weighted-BCE head needs d_coef"); return -1; }
+    B2S_TRY(enter(p));
+    cudaStream_t st = p->stream;
+    p->batch = batch;
+    p->loss_scale = loss_scale;
+    p->v_is_current = false;
+    B2S_CUDA(cudaMemcpyAsync(p->params, d_params, (size_t)p->P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const b2s_tensor& X = p->tensors[0];
+    B2S_CUDA(cudaMemcpyAsync(p->fw[0] + p->buf_off[X.buf], d_x, (size_t)batch * p->buf_elems[X.buf] * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    if (wbce) {
+        const size_t nb = (size_t)batch * p->n_classes * sizeof(float);
+        B2S_CUDA(cudaMemcpyAsync(p->target, d_y, nb, cudaMemcpyDeviceToDevice, st));
+        B2S_CUDA(cudaMemcpyAsync(p->coef, d_coef, nb, cudaMemcpyDeviceToDevice, st));
+    } else {
+        B2S_CUDA(cudaMemcpyAsync(p->labels, d_y, (size_t)batch * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+    }
+    const int rc = run_pass(p, 4);
+    if (rc != 0) { p->batch = 0; return rc; }
+    if (d_logits_out) {
+        const b2s_tensor& L = p->tensors[p->logits];
+        const size_t row = (size_t)L.C * L.H * L.W * sizeof(float);
+        B2S_CUDA(cudaMemcpy2DAsync(d_logits_out, row, tptr(p, p->fw, 0, p->logits), (size_t)L.sample_stride * sizeof(float),
+                                   row, (size_t)batch, cudaMemcpyDeviceToDevice, st));
+    }
+    if (d_loss_out) B2S_CUDA(cudaMemcpyAsync(d_loss_out, p->loss, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    p->batch = 0;
     return leave(p);
 }
 
@@ -1150,6 +1241,125 @@ int b2s_pi_result(b2s_pistate* s, b2s_power_result* r, double* h_traj, double* d
 
 static int kfac_apply_impl(b2s_plan* p, const double* d_r, double* d_out);
 
+namespace b2s {
+__global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const PiDev* S) {
+    cudaGraphSetConditional(handle, S->done ? 0u : 1u);
+}
+}  // namespace b2s
+
+// The whole eigen-iteration as ONE graph launch: a WHILE conditional node whose body is the order-1 pass plus
+// the two vector kernels; the last kernel of the body feeds the device-side `done` flag to the condition.  No host
+// round trip per iteration (the reference does >= 5 `.item()` syncs per iteration, opt.py:457-464) and no work
+// after convergence.  Returns 0 = ran, 1 = not available here (caller uses the polled loop), < 0 = error.
+static int power_loop_on_device(b2s_plan* p, b2s_pistate* s) {
+    if (p->device_loop < 0) {
+        const char* e = getenv("B2S_DEVICE_LOOP");
+        p->device_loop = (e && atoi(e) == 0) || !p->use_graphs || p->comm ? 0 : 1;
+        if (!p->device_loop) return 1;
+    }
+    cudaStream_t st = p->stream;
+    auto it = p->loops.find(p->batch);
+    if (it != p->loops.end() && (it->second.loss_scale != p->loss_scale || it->second.global_batch != p->global_batch)) {
+        if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+        p->loops.erase(it);
+        it = p->loops.end();
+    }
+    if (it == p->loops.end()) {
+        cudaGraph_t graph = nullptr;
+        b2s_plan::LoopGraph lg;
+        bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+        cudaGraphConditionalHandle handle{};
+        ok = ok && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        cudaGraphNodeParams np{};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node = nullptr;
+        ok = ok && cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+        int rc = 0;
+        if (ok) {
+            cudaGraph_t body = np.conditional.phGraph_out[0];
+            g_counting_paused = true;
+            g_capture_count = 0;
+            ok = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                rc = run_pass_eager(p, 1);
+                if (rc == 0) rc = launch_pi_step(st, s->d, s->n, p->out32[1]);
+                if (rc == 0) {
+                    loop_condition_kernel<<<1, 1, 0, st>>>(handle, s->d);
+                    count_launch();
+                }
+                cudaGraph_t out = nullptr;
+                ok = cudaStreamEndCapture(st, &out) == cudaSuccess && rc == 0;
+            }
+            g_counting_paused = false;
+            lg.kernels_per_iter = g_capture_count;
+        }
+        ok = ok && cudaGraphInstantiate(&lg.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            // conditional nodes unavailable (driver) or a node kind the body does not admit: polled loop from now on
+            cudaGetLastError();
+            p->device_loop = 0;
+            if (rc < 0 && rc != -2) return rc;
+            // the failed capture may have left the pass half enqueued nowhere; the state was not advanced
+            return 1;
+        }
+        lg.loss_scale = p->loss_scale;
+        lg.global_batch = p->global_batch;
+        it = p->loops.emplace(p->batch, lg).first;
+    }
+    B2S_CUDA(cudaGraphLaunch(it->second.exec, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    int last = -1;
+    B2S_CUDA(cudaMemcpy(&last, &s->d->last_iter, sizeof(int), cudaMemcpyDeviceToHost));
+    count_launch((int)(it->second.kernels_per_iter * (last + 1)));
+    return 0;
+}
+
+// Host-driven loop (data parallel runs, eager mode): the `done` flag is read back with a lag of a few iterations so
+// that the device queue never drains on short iterations; every kernel of the loop is gated on the flag, so the
+// iterations enqueued past convergence change nothing.
+static int power_loop_polled(b2s_plan* p, b2s_pistate* s, int max_iter) {
+    cudaStream_t st = p->stream;
+    if (!p->h_done) {
+        B2S_CUDA(cudaHostAlloc(&p->h_done, (b2s_plan::kMaxLag + 1) * sizeof(int), cudaHostAllocDefault));
+        for (auto& e : p->ev_poll) B2S_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int lag = p->poll_lag;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (lag < 0) {
+        if (const char* e = getenv("B2S_POLL_LAG")) p->poll_lag = std::max(0, std::min((int)b2s_plan::kMaxLag, atoi(e)));
+        lag = 0;                                   // first call: synchronous, and the first iteration is timed
+        if (p->poll_lag < 0) {
+            cudaEventCreate(&t0); cudaEventCreate(&t1);
+        }
+    }
+    const int ring = b2s_plan::kMaxLag + 1;
+    for (int it = 0; it < max_iter; ++it) {
+        if (t0 && it == 1) cudaEventRecord(t0, st);
+        B2S_TRY(run_pass(p, 1));
+        B2S_TRY(launch_pi_step(st, s->d, s->n, p->out32[1]));
+        if (t0 && it == 1) cudaEventRecord(t1, st);
+        B2S_CUDA(cudaMemcpyAsync(&p->h_done[it % ring], &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B2S_CUDA(cudaEventRecord(p->ev_poll[it % ring], st));
+        if (it >= lag) {
+            const int w = (it - lag) % ring;
+            B2S_CUDA(cudaEventSynchronize(p->ev_poll[w]));
+            if (p->h_done[w]) break;
+        }
+    }
+    if (t0) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t1) == cudaSuccess && cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess && ms > 0.f)
+            p->poll_lag = ms < 0.03f ? 4 : ms < 0.12f ? 2 : ms < 0.5f ? 1 : 0;     // keep ~100 us of work queued
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    }
+    return 0;
+}
+
+
 int b2s_power_iterate(b2s_plan* p, double* d_v, const b2s_power_cfg* cfg, b2s_power_result* h_result,
                       double* h_traj) {
     if (!p || !d_v || !cfg) { set_error("b2s_power_iterate: null argument"); return -1; }
@@ -1168,22 +1378,28 @@ int b2s_power_iterate(b2s_plan* p, double* d_v, const b2s_power_cfg* cfg, b2s_po
     b2s_pistate* s = p->pi;
     cudaStream_t st = p->stream;
     B2S_TRY(pi_reset_impl(s, d_v, cfg, st));
-    int done = cfg->max_iter <= 0;
-    while (!done) {
-        // the HVP reads p->v32, which pass B of the previous iteration wrote (the state aliases it)
-        B2S_TRY(run_pass(p, 1));
-        B2S_TRY(launch_pi_step(st, s->d, s->n, p->out32[1]));
-        B2S_CUDA(cudaMemcpyAsync(&done, &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-        B2S_CUDA(cudaStreamSynchronize(st));
-        if (cfg->precond && !done) {                          // v <- normalise(v + alpha T r)   opt.py:491-498
-            PiDev h;
+    B2S_TRY(alloc_order(p, 1));
+    if (cfg->precond) {
+        int done = cfg->max_iter <= 0;
+        while (!done) {
+            // the HVP reads p->v32, which the previous iteration's update wrote (the state aliases it)
+            B2S_TRY(run_pass(p, 1));
+            B2S_TRY(launch_pi_step(st, s->d, s->n, p->out32[1]));
+            PiDev h;                                              // v <- normalise(v + alpha T r)   opt.py:491-498
             B2S_CUDA(cudaMemcpyAsync(&h, s->d, sizeof(PiDev), cudaMemcpyDeviceToHost, st));
             B2S_CUDA(cudaStreamSynchronize(st));
-            B2S_TRY(kfac_apply_impl(p, s->rbuf[h.r_last], p->kfac_tr));
-            B2S_TRY(launch_pi_precond_update(st, s->d, s->n, p->kfac_tr));
-            B2S_CUDA(cudaMemcpyAsync(&done, &s->d->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-            B2S_CUDA(cudaStreamSynchronize(st));
+            done = h.done;
+            if (!done) {
+                B2S_TRY(kfac_apply_impl(p, s->rbuf[h.r_last], p->kfac_tr));
+                B2S_TRY(launch_pi_precond_update(st, s->d, s->n, p->kfac_tr));
+                done = h.iter >= h.max_iter;                      // what pi_precond_commit_kernel decides
+            }
         }
+    } else if (cfg->max_iter > 0) {
+        int rc = 1;
+        if (p->device_loop != 0) rc = power_loop_on_device(p, s);
+        if (rc < 0) return rc;
+        if (rc == 1) B2S_TRY(power_loop_polled(p, s, cfg->max_iter));
     }
     p->v_is_current = false;
     B2S_TRY(pi_result_impl(s, h_result, h_traj, d_v, st));
@@ -1215,9 +1431,11 @@ int b2s_kfac_build(b2s_plan* p, int32_t op_a, int32_t op_g, float* d_A, float* d
     B2S_TRY(kfac_dims(p, op_g, nullptr, &dg, nullptr));
     if (!d_A || !d_G) { set_error("b2s_kfac_build: null output"); return -1; }
     if (p->batch <= 0) { set_error("b2s_kfac_build: call b2s_base_pass first"); return -1; }
-    if (p->world > 1) { set_error("b2s_kfac_build: the preconditioned variant runs on one GPU"); return -1; }
     B2S_TRY(enter(p));
     cudaStream_t st = p->stream;
+    // data parallel: the factors are batch means, so every rank adds its samples' share and 1/world of
+    // the identity term, then one all-reduce per factor; eigh and the apply stay replicated
+    const long long gb = p->global_batch > 0 ? p->global_batch : (long long)p->batch * p->world;
     {   // A = 0.95 I + 0.05 a^T a / B, a = patches / spatial with a ones column (kfac.py:292-311, 52-58)
         const b2s_op& op = p->ops[op_a];
         const b2s_tensor& I = p->tensors[op.in];
@@ -1225,14 +1443,16 @@ int b2s_kfac_build(b2s_plan* p, int32_t op_a, int32_t op_g, float* d_A, float* d
         const float S = (float)(O.H * O.W);
         B2S_TRY(launch_gram(st, tptr(p, p->fw, 0, op.in), I.sample_stride, p->batch, I.C, I.H, I.W, O.H, O.W, op.kh, op.kw,
                             op.sh, op.sw, op.ph, op.pw, op.b_off >= 0 ? 1 : 0, 1.f / S, 1.f / S,
-                            0.05f / (float)p->batch, 0.95f, d_A));
+                            0.05f / (float)gb, 0.95f / (float)p->world, d_A));
+        if (p->comm) B2S_TRY(comm_allreduce_f32(p->comm, d_A, (long long)da * da, st));
     }
     {   // G = 0.95 I + 0.05 * B*S * g^T g  (kfac.py:337-367 with batch_averaged=True, 60-65)
         const b2s_op& op = p->ops[op_g];
         const b2s_tensor& O = p->tensors[op.out];
         const float S = (float)(O.H * O.W);
         B2S_TRY(launch_gram(st, tptr(p, p->bw, 0, op.out), O.sample_stride, p->batch, O.C, O.H, O.W, O.H, O.W, 1, 1, 1, 1,
-                            0, 0, 0, 1.f, 0.f, 0.05f * (float)p->batch * S, 0.95f, d_G));
+                            0, 0, 0, 1.f, 0.f, 0.05f * (float)gb * S, 0.95f / (float)p->world, d_G));
+        if (p->comm) B2S_TRY(comm_allreduce_f32(p->comm, d_G, (long long)dg * dg, st));
     }
     return leave(p);
 }
@@ -1292,13 +1512,45 @@ int b2s_step_assemble(const double* d_gradf, const double* d_gradrho, double coe
     return launch_step_assemble((cudaStream_t)stream, d_gradf, d_gradrho, coef, (long long)n, d_p, d_p32);
 }
 
+int b2s_clip_norm(const double* d_x, int64_t n, double clip, double* d_scratch, double* d_out2, void* stream) {
+    if (!d_x || !d_scratch || !d_out2 || n <= 0) { set_error("b2s_clip_norm: null argument"); return -1; }
+    return launch_clip_norm((cudaStream_t)stream, d_x, (long long)n, clip, d_scratch, d_out2);
+}
+
+int b2s_clip_scratch_doubles(void) { return pi_scratch_doubles() + 2; }
+
+int b2s_step_fused(const double* d_gradf, double* d_gradrho, double coef, const double* d_scale2, int64_t n, double* d_p,
+                   float* d_p32, float* d_params, float* d_state1, float* d_state2, const b2s_step_opt* opt, void* stream) {
+    if (!d_gradf || !d_p32 || !opt || n <= 0) { set_error("b2s_step_fused: null argument"); return -1; }
+    if (opt->kind < 0 || opt->kind > 2) { set_error("b2s_step_fused: optimizer kind %d", opt->kind); return -1; }
+    if (opt->kind != 0 && !d_params) { set_error("b2s_step_fused: optimizer update without a parameter vector"); return -1; }
+    if ((opt->kind == 1 && opt->momentum != 0.0 && !d_state1) || (opt->kind == 2 && (!d_state1 || !d_state2))) {
+        set_error("b2s_step_fused: optimizer state vector missing");
+        return -1;
+    }
+    StepOpt o{};
+    o.kind = opt->kind; o.first = opt->first_step; o.nesterov = opt->nesterov; o.maximize = opt->maximize;
+    o.write_gradrho = opt->write_gradrho;
+    o.lr = (float)opt->lr; o.momentum = (float)opt->momentum; o.dampening = (float)opt->dampening;
+    o.weight_decay = (float)opt->weight_decay;
+    o.beta1 = (float)opt->beta1; o.beta2 = (float)opt->beta2; o.eps = (float)opt->eps;
+    o.step_size = (float)opt->step_size; o.bias2_sqrt = (float)opt->bias2_sqrt;
+    return launch_step_fused((cudaStream_t)stream, d_gradf, d_gradrho, coef, d_scale2, (long long)n, d_p, d_p32, d_params,
+                             d_state1, d_state2, o);
+}
+
+int b2s_plan_set_global_batch(b2s_plan* p, int64_t global_batch) {
+    if (!p || global_batch < 0) { set_error("b2s_plan_set_global_batch: invalid arguments"); return -1; }
+    p->global_batch = global_batch;              // graphs captured with another count are re-captured on use
+    return 0;
+}
+
 int b2s_comm_unique_id(void* h_id128) { return comm_unique_id(h_id128); }
 int b2s_comm_init(b2s_plan* p, const void* h_id128, int32_t rank, int32_t world) {
     if (!p || !h_id128) { set_error("b2s_comm_init: null argument"); return -1; }
     B2S_CUDA(cudaSetDevice(p->device));
     if (p->comm) { comm_destroy(p->comm); p->comm = nullptr; }
-    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    p->graphs.clear();
+    drop_graphs(p);
     p->world = world;
     if (world <= 1) return 0;
     return comm_init(&p->comm, h_id128, rank, world);
@@ -1313,15 +1565,13 @@ int b2s_comm_peer_attach(b2s_plan* p, const void* h_handles) {
     if (!p || !h_handles) { set_error("b2s_comm_peer_attach: null argument"); return -1; }
     if (!p->comm) { set_error("b2s_comm_peer_attach: call b2s_comm_init first"); return -1; }
     B2S_CUDA(cudaSetDevice(p->device));
-    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    p->graphs.clear();
+    drop_graphs(p);
     return comm_peer_attach(p->comm, h_handles);
 }
 int b2s_comm_peer_ready(const b2s_plan* p) { return (p && p->comm) ? comm_peer_ready(p->comm) : 0; }
 int b2s_comm_peer_disable(b2s_plan* p) {
     if (!p || !p->comm) return 0;
-    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    p->graphs.clear();
+    drop_graphs(p);
     comm_peer_disable(p->comm);
     return 0;
 }
@@ -1329,8 +1579,7 @@ int b2s_comm_destroy(b2s_plan* p) {
     if (!p) return 0;
     if (p->comm) { comm_destroy(p->comm); p->comm = nullptr; }
     p->world = 1;
-    for (auto& kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    p->graphs.clear();
+    drop_graphs(p);
     return 0;
 }
 

@@ -309,4 +309,88 @@ int launch_step_assemble(cudaStream_t st, const double* gf, const double* gr, do
     return 0;
 }
 
+
+// ---- fused regularised step (opt.py:535-542, 616-659, 696-699) ---------------------------------------------
+// The rest of iter()'s minibatch body on flat vectors: the clip of grad rho (norm from a first pass, scale kept on
+// the device: no host sync), p = grad f + mu * sign * grad rho, its fp32 rounding (= param.grad), and the
+// optimizer update (torch.optim.SGD with momentum / dampening / nesterov / weight decay, or torch.optim.Adam) applied
+// in place to the flat fp32 parameter vector that the model's parameters are views of -- one kernel instead of the
+// reference's per-parameter Python loop plus the optimizer's own per-tensor kernels.
+__global__ void __launch_bounds__(kVecThreads) clip_norm_kernel(const double* __restrict__ x, const long long n, const double clip,
+                                                                double* __restrict__ scratch, unsigned* __restrict__ counter,
+                                                                double* __restrict__ out2) {
+    __shared__ double red[32];
+    double acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc += x[i] * x[i];
+    double part[1] = {acc};
+    block_sum<1, double>(part, red);
+    if (threadIdx.x == 0) scratch[blockIdx.x] = part[0];
+    if (!last_block_arrives(counter)) return;
+    double tot[1];
+    final_sum<1>(scratch, tot, red);
+    if (threadIdx.x == 0) {
+        const double nrm = sqrt(tot[0]);
+        out2[0] = nrm;
+        out2[1] = (clip > 0 && nrm > clip) ? clip / nrm : 1.0;      // opt.py:539-542
+    }
+}
+
+__global__ void __launch_bounds__(256) step_fused_kernel(const double* __restrict__ gf, double* __restrict__ gr, const double coef,
+                                                         const double* __restrict__ scale2, const long long n, double* __restrict__ p64,
+                                                         float* __restrict__ p32, float* __restrict__ w, float* __restrict__ s1,
+                                                         float* __restrict__ s2, const StepOpt o) {
+    const double sc = (gr && scale2) ? scale2[1] : 1.0;
+    const double cs = coef * sc;
+    const bool rescale = gr && sc != 1.0 && o.write_gradrho;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double a = gf[i];
+        if (gr) {
+            const double b = gr[i];
+            a += cs * b;
+            if (rescale) gr[i] = sc * b;
+        }
+        if (p64) p64[i] = a;
+        float g = (float)a;                      // param.grad = p[i:i+n].view(s).float()   opt.py:658
+        p32[i] = g;
+        if (o.kind == 0) continue;
+        float x = w[i];
+        if (o.maximize) g = -g;
+        if (o.weight_decay != 0.f) g = g + o.weight_decay * x;
+        if (o.kind == 1) {                       // torch.optim.SGD (_single_tensor_sgd)
+            if (o.momentum != 0.f) {
+                float b = o.first ? g : o.momentum * s1[i] + (1.f - o.dampening) * g;
+                s1[i] = b;
+                g = o.nesterov ? g + o.momentum * b : b;
+            }
+            w[i] = x - o.lr * g;
+        } else {                                 // torch.optim.Adam (_single_tensor_adam, amsgrad = False)
+            float m = s1[i], v = s2[i];
+            m = m + (g - m) * (1.f - o.beta1);
+            v = o.beta2 * v + (1.f - o.beta2) * g * g;
+            s1[i] = m; s2[i] = v;
+            const float denom = sqrtf(v) / o.bias2_sqrt + o.eps;
+            w[i] = x - o.step_size * (m / denom);
+        }
+    }
+}
+
+int launch_clip_norm(cudaStream_t st, const double* x, long long n, double clip, double* scratch, double* out2) {
+    const int blocks = vec_blocks(n);
+    unsigned* counter = reinterpret_cast<unsigned*>(scratch + kVecBlocksMax);
+    clip_norm_kernel<<<blocks, kVecThreads, 0, st>>>(x, n, clip, scratch, counter, out2);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_step_fused(cudaStream_t st, const double* gf, double* gr, double coef, const double* scale2, long long n, double* p64,
+                      float* p32, float* w, float* s1, float* s2, const StepOpt& o) {
+    int blocks = cdiv(n, 256 * 2);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    step_fused_kernel<<<blocks, 256, 0, st>>>(gf, gr, coef, scale2, n, p64, p32, w, s1, s2, o);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace b2s

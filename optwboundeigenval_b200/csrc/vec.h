@@ -31,4 +31,17 @@ int launch_pi_precond_update(cudaStream_t st, PiDev* dS, long long n, const doub
 // p64 (optional) = gf + coef * gr (gr optional), p32 = (float)p64 : the step assembly of opt.py:616-659
 int launch_step_assemble(cudaStream_t st, const double* gf, const double* gr, double coef, long long n, double* p64, float* p32);
 
+
+struct StepOpt {
+    int kind;               // 0: assemble only, 1: SGD, 2: Adam
+    int first;              // SGD: momentum buffers are initialised by this step (torch: buf = clone(grad))
+    int nesterov, maximize, write_gradrho;
+    float lr, momentum, dampening, weight_decay;
+    float beta1, beta2, eps, step_size, bias2_sqrt;     // Adam: step_size = lr / (1 - beta1^t), bias2_sqrt = sqrt(1 - beta2^t)
+};
+// out2 = {|x|, clip > 0 && |x| > clip ? clip / |x| : 1}; scratch: pi_scratch_doubles() + 1 doubles, zero-initialised once
+int launch_clip_norm(cudaStream_t st, const double* x, long long n, double clip, double* scratch, double* out2);
+int launch_step_fused(cudaStream_t st, const double* gf, double* gr, double coef, const double* scale2, long long n, double* p64,
+                      float* p32, float* w, float* s1, float* s2, const StepOpt& o);
+
 }  // namespace b2s

@@ -8,6 +8,9 @@ What is replaced (all resolved at call time by the reference, so no source edit 
 
 * ``opt.HVPOperator``  ->  ``B200HVPOperator``           (constructed per minibatch at opt.py:424)
 * ``OptWBoundEignVal.comp_rho / comp_gradrho``  ->  fused device loop (``spectral.py``)
+* ``OptWBoundEignVal.comp_f``  ->  forward-only evaluation pass (``b2s_eval_pass``); ``test_model`` reaches it unchanged
+* ``OptWBoundEignVal.iter``  ->  ``spectral.iter_epoch``: the same epoch with the minibatch body's clip, step assembly
+  and SGD / Adam update fused on flat vectors (opt.py:535-542, 616-659, 696-699)
 * ``OptWBoundEignVal.__init__``: ``use_gpu`` is forced on -- many parameter files say
   ``use_gpu=False`` (forest_best.py:43, usps_CNN_lobpcg.py:52, chestxray_best_reg.py:110) and the
   B200 path has no CPU variant; with it the trainer keeps model, ``self.v`` and gradients on the device.
@@ -28,6 +31,16 @@ import numpy as np
 import torch
 
 
+def find_reference():
+    """A directory holding the reference's ``opt.py``: ``$OPTW_REFERENCE``, ``/root/reference``, or the copy under
+    ``baseline/_ref/optWBoundEigenval`` next to this package (None when there is none)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for c in (os.environ.get("OPTW_REFERENCE"), "/root/reference", os.path.join(root, "baseline", "_ref", "optWBoundEigenval")):
+        if c and os.path.exists(os.path.join(c, "opt.py")):
+            return os.path.abspath(c)
+    return None
+
+
 def install(opt_module, fused_loop: bool = True, force_gpu: bool = True):
     """Patch the reference module in place; returns a dict of the originals for ``uninstall``."""
     from . import spectral
@@ -41,12 +54,24 @@ def install(opt_module, fused_loop: bool = True, force_gpu: bool = True):
         saved.update({"kfac": cls.kfac, "init_kfac": cls.init_kfac})
         cls.comp_rho = spectral.comp_rho
         cls.comp_gradrho = spectral.comp_gradrho
+        saved["comp_f"] = cls.comp_f
+        cls.comp_f = spectral.comp_f
         cls.kfac = _kfac.kfac
         cls.init_kfac = _kfac.init_kfac
         # additions (no reference method is replaced): the fused step assembly of iter()'s minibatch body and the
         # replicas-only multi-GPU form of the rho_test sweep
         cls.assemble_step = spectral.assemble_step
+        cls.fused_step = spectral.fused_step
         cls.rho_sweep = spectral.rho_test
+        # iter() (opt.py:580-763): same epoch, minibatch body = comp_g + fused clip / assembly / optimizer update; the
+        # branches that are not the plain power-iteration step run the reference's own iter()
+        saved["iter"] = reference_iter = cls.iter
+
+        def iter(self):
+            import types
+            self._b200_reference_iter = types.MethodType(reference_iter, self)
+            return spectral.iter_epoch(self)
+        cls.iter = iter
     if force_gpu:
         orig_init = cls.__init__
 
@@ -79,7 +104,8 @@ def uninstall(opt_module):
     cls.comp_rho, cls.comp_gradrho, cls.__init__ = saved["comp_rho"], saved["comp_gradrho"], saved["__init__"]
     if "kfac" in saved:
         cls.kfac, cls.init_kfac = saved["kfac"], saved["init_kfac"]
-        for extra in ("assemble_step", "rho_sweep"):
+        cls.iter, cls.comp_f = saved["iter"], saved["comp_f"]
+        for extra in ("assemble_step", "fused_step", "rho_sweep"):
             if extra in cls.__dict__:
                 delattr(cls, extra)
     del opt_module._b200_saved

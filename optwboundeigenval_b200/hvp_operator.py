@@ -73,6 +73,9 @@ class SpectralPlan:
         self._bn_ptrs = None
         self.world = 1
         self.rank = 0
+        self.owner = None                 # weakref of the operator whose base pass is cached (see B200HVPOperator._own)
+        self.global_batch = 0
+        self._vin = None                  # staging vector for host inputs (fp64, device)
         self._finalizer = weakref.finalize(self, SpectralPlan._destroy, self.lib, handle)
 
     @staticmethod
@@ -122,6 +125,40 @@ class SpectralPlan:
         return t.contiguous(), coef.contiguous()
 
     # ---- passes -----------------------------------------------------------------------------
+    def _head_inputs(self, target, batch, gbatch, use_global):
+        head = self.tape.head
+        if head in (HEAD_CE, HEAD_SOFTMAX_CE):
+            return target.to(self.device, torch.int64).contiguous().view(-1), None, 1.0 / float(gbatch)
+        t = target.to(self.device, torch.float32)
+        if t.dim() == 1:
+            t = t.view(-1, 1)
+        y, coef = self.wbce_coefficients(t, self._global_sums if use_global else None)
+        return y, coef, 1.0
+
+    def eval_pass(self, params: torch.Tensor, x: torch.Tensor, target: torch.Tensor):
+        """comp_f (opt.py:544-572): forward only, evaluation-mode BatchNorm; returns (loss fp64 [1], model output
+        [batch, classes] fp32) device tensors -- the output with the model's own softmax / sigmoid tail applied,
+        as ``self.model(inputs)`` returns it.  Local to this rank; the cached base pass is forgotten."""
+        batch = int(x.shape[0])
+        if batch > self.max_batch:
+            raise RuntimeError("batch %d exceeds the plan's max_batch %d" % (batch, self.max_batch))
+        self._bind_stream()
+        self._bind_bn()
+        x = x.to(self.device, torch.float32).contiguous()
+        y, coef, scale = self._head_inputs(target, batch, batch, False)
+        nc = self.tape.tensors[self.tape.logits].numel
+        logits = torch.empty(batch, nc, dtype=torch.float32, device=self.device)
+        loss = torch.empty(1, dtype=torch.float64, device=self.device)
+        self.owner = None
+        _lib.check(self.lib.b2s_eval_pass(self.handle, _ptr(params), _ptr(x), _ptr(y), _ptr(coef), batch, scale,
+                                          _ptr(logits), _ptr(loss)), "b2s_eval_pass")
+        self._keep = (params, x, y, coef)
+        if self.tape.head == HEAD_SOFTMAX_CE:
+            logits = torch.softmax(logits, dim=1)
+        elif self.tape.head == HEAD_SIGMOID_WBCE:
+            logits = torch.sigmoid(logits)
+        return loss, logits
+
     def base_pass(self, params: torch.Tensor, x: torch.Tensor, target: torch.Tensor):
         """forward + loss + gradient; returns (grad fp64 [P], loss fp64 [1]) device tensors."""
         batch = int(x.shape[0])
@@ -130,17 +167,16 @@ class SpectralPlan:
         self._bind_stream()
         self._bind_bn()
         x = x.to(self.device, torch.float32).contiguous()
-        head = self.tape.head
-        coef = None
-        if head in (HEAD_CE, HEAD_SOFTMAX_CE):
-            y = target.to(self.device, torch.int64).contiguous().view(-1)
-            scale = 1.0 / float(batch * self.world)
-        else:
-            t = target.to(self.device, torch.float32)
-            if t.dim() == 1:
-                t = t.view(-1, 1)
-            y, coef = self.wbce_coefficients(t, self._global_sums if self.world > 1 else None)
-            scale = 1.0
+        gbatch = batch
+        if self.world > 1:
+            # shards may be ragged (the last minibatch of a per-rank loader): weigh by the global sample count
+            import torch.distributed as dist
+            nb = torch.tensor([batch], dtype=torch.int64, device=self.device)
+            dist.all_reduce(nb)
+            gbatch = int(nb.item())
+            _lib.check(self.lib.b2s_plan_set_global_batch(self.handle, gbatch), "b2s_plan_set_global_batch")
+        self.global_batch = gbatch
+        y, coef, scale = self._head_inputs(target, batch, gbatch, self.world > 1)
         grad = torch.empty(self.P, dtype=torch.float64, device=self.device)
         loss = torch.empty(1, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.b2s_base_pass(self.handle, _ptr(params), _ptr(x), _ptr(y), _ptr(coef), batch, scale,
@@ -276,8 +312,68 @@ def clear_plans():
     _PLANS.clear()
 
 
+class FlatParams(object):
+    """One persistent flat fp32 vector per model in ``model.parameters()`` order (the layout of every spectral
+    vector, opt.py:102,191).
+
+    ``gather()`` refreshes it with ONE multi-tensor copy instead of a ``torch.cat`` of 119..364 tensors per
+    minibatch.  ``attach()`` goes further and makes every ``param.data`` a view INTO the vector (what
+    DistributedDataParallel does with its buckets): gathering becomes free and the fused optimizer step
+    (``spectral.fused_step``) updates the parameters in place on the flat vector.  Parameter objects, their
+    identity and ``state_dict`` keys are unchanged; an attachment broken from outside (``param.data = ...``,
+    ``model.to(...)``) is detected by pointer comparison and redone."""
+
+    def __init__(self, model, device):
+        self.params = [q for q in model.parameters()]
+        self.sizes = [q.numel() for q in self.params]
+        self.n = sum(self.sizes)
+        self.flat = torch.empty(self.n, dtype=torch.float32, device=device)
+        self.views, self.offsets = [], []
+        i = 0
+        for q, n in zip(self.params, self.sizes):
+            self.views.append(self.flat[i:i + n].view(q.shape))
+            self.offsets.append(i)
+            i += n
+        self.attached = False
+
+    def matches(self, model):
+        ps = list(model.parameters())
+        return len(ps) == len(self.params) and all(a is b for a, b in zip(ps, self.params))
+
+    def is_attached(self):
+        base, es = self.flat.data_ptr(), self.flat.element_size()
+        return self.attached and all(q.dtype == torch.float32 and q.data_ptr() == base + o * es and q.is_contiguous()
+                                     for q, o in zip(self.params, self.offsets))
+
+    def gather(self) -> torch.Tensor:
+        if not self.is_attached():
+            self.attached = False
+            torch._foreach_copy_(self.views, [q.detach() for q in self.params])
+        return self.flat
+
+    def attach(self) -> torch.Tensor:
+        if not self.is_attached():
+            with torch.no_grad():
+                torch._foreach_copy_(self.views, [q.detach() for q in self.params])
+                for q, v in zip(self.params, self.views):
+                    q.data = v
+            self.attached = True
+        return self.flat
+
+
+_FLAT = weakref.WeakKeyDictionary()
+
+
+def flat_params_of(model, device) -> FlatParams:
+    fp = _FLAT.get(model)
+    if fp is None or fp.flat.device != device or not fp.matches(model):
+        fp = _FLAT[model] = FlatParams(model, device)
+    return fp
+
+
 def flat_parameters(model) -> torch.Tensor:
-    return torch.cat([p.detach().reshape(-1) for p in model.parameters()]).float().contiguous()
+    dev = next(model.parameters()).device
+    return flat_params_of(model, dev).gather()
 
 
 class B200HVPOperator(object):
@@ -298,6 +394,9 @@ class B200HVPOperator(object):
         self.aTime0 = self.aTime1 = self.aTime2 = 0
         self.plan: Optional[SpectralPlan] = None
         self.loss_value = None
+        # True: a PINNED host vector is copied to the device without waiting on the host (the caller must not
+        # overwrite it before the call's result has been synchronised); False: torch's blocking semantics
+        self.async_host_vectors = False
 
     # -- housekeeping, same behaviour as the reference (opt.py:72-75,154-173) --
     def mem_check(self):
@@ -323,6 +422,14 @@ class B200HVPOperator(object):
     def _vec(self, vec):
         if type(vec) is np.ndarray:
             vec = torch.from_numpy(vec)
+        if vec.is_cuda and vec.dtype == torch.float64 and vec.is_contiguous():
+            return vec
+        if not vec.is_cuda and vec.dtype == torch.float64 and self.plan is not None and vec.numel() == self.plan.P:
+            # host vector: one copy into the plan's staging vector (no allocation, no second cast kernel)
+            if self.plan._vin is None:
+                self.plan._vin = torch.empty(self.plan.P, dtype=torch.float64, device=self.device)
+            self.plan._vin.copy_(vec.reshape(-1), non_blocking=self.async_host_vectors and vec.is_pinned())
+            return self.plan._vin
         return vec.to(self.device).double().contiguous()
 
     # -- the three entry points --
@@ -337,6 +444,7 @@ class B200HVPOperator(object):
         nbt = [m.num_batches_tracked for m in self.plan.tape.bn_modules if m.num_batches_tracked is not None]
         if nbt:                                       # train-mode forward side effect
             torch._foreach_add_(nbt, 1)
+        self.plan.owner = weakref.ref(self)
         self.aTime0 += time.time() - start
         self.loss_value = loss
         return grad
@@ -345,10 +453,31 @@ class B200HVPOperator(object):
         if not (storedGrad and self.stored_grad is not None):
             self.zero_grad()
             self.stored_grad = self.prepare_grad()
+        elif self.plan.owner is None or self.plan.owner() is not self:
+            self._own()
+
+    def _own(self):
+        """All operators of one (model, loss, input shape) share a plan, whose caches hold the LAST base pass.  The
+        reference's operators are independent objects (each keeps its own graph, opt.py:175-192), so when another
+        operator -- or init_kfac -- ran a base pass in between, this operator's minibatch is passed again before its
+        Hv / vGHv; the train-mode side effects of that repeat (BatchNorm running statistics, num_batches_tracked)
+        are undone, because the reference would not have run a second forward."""
+        bns = self.plan.tape.bn_modules
+        saved = [(m.running_mean.clone(), m.running_var.clone(),
+                  m.num_batches_tracked.clone() if m.num_batches_tracked is not None else None) for m in bns]
+        a0 = self.aTime0
+        self.prepare_grad()
+        self.aTime0 = a0
+        with torch.no_grad():
+            for m, (rm, rv, nb) in zip(bns, saved):
+                m.running_mean.copy_(rm)
+                m.running_var.copy_(rv)
+                if nb is not None:
+                    m.num_batches_tracked.copy_(nb)
 
     def Hv(self, vec, storedGrad=False):
-        vec = self._vec(vec)
         self._ensure_grad(storedGrad)
+        vec = self._vec(vec)
         self.mem_check()
         start = time.time()
         out = self.plan.hv(vec)
@@ -357,8 +486,8 @@ class B200HVPOperator(object):
         return out
 
     def vGHv(self, vec, storedGrad=False):
-        vec = self._vec(vec)
         self._ensure_grad(storedGrad)
+        vec = self._vec(vec)
         self.mem_check()
         start = time.time()
         out = self.plan.vghv(vec)

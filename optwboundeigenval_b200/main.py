@@ -19,7 +19,7 @@ import sys
 import tempfile
 
 
-def run(pfile, reference, offline=False, overrides=None, workdir=None, install=True):
+def run(pfile, reference, offline=False, overrides=None, workdir=None, install=True, n_train=512, n_eval=128):
     from . import dropin
     reference = os.path.abspath(reference)
     if not os.path.exists(os.path.join(reference, "opt.py")):
@@ -29,7 +29,7 @@ def run(pfile, reference, offline=False, overrides=None, workdir=None, install=T
         sys.path.insert(0, reference)
     import opt  # noqa: E402  (the reference module)
     if offline:
-        dropin.offline_shims(reference)
+        dropin.offline_shims(reference, n_train=n_train, n_eval=n_eval)
     if install:
         dropin.install(opt)
     workdir = workdir or tempfile.mkdtemp(prefix="b200_run_")
@@ -72,13 +72,16 @@ def _parse_overrides(items):
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__)
     ap.add_argument("pfile")
-    ap.add_argument("--reference", default=os.environ.get("OPTW_REFERENCE", "."))
+    from . import dropin
+    ap.add_argument("--reference", default=dropin.find_reference() or ".")
     ap.add_argument("--offline", action="store_true")
     ap.add_argument("--set", nargs="*", default=[])
     ap.add_argument("--workdir", default=None)
     ap.add_argument("--no-install", action="store_true")
+    ap.add_argument("--n-train", type=int, default=512, help="--offline: synthetic training samples")
+    ap.add_argument("--n-eval", type=int, default=128, help="--offline: synthetic validation / test samples")
     a = ap.parse_args(argv)
-    wd = run(a.pfile, a.reference, a.offline, _parse_overrides(a.set), a.workdir, not a.no_install)
+    wd = run(a.pfile, a.reference, a.offline, _parse_overrides(a.set), a.workdir, not a.no_install, a.n_train, a.n_eval)
     print("logs and models under", wd)
 
 

@@ -2,6 +2,8 @@
 keys the driver reads, and the B200 arm refuses to run without a CUDA device (no CPU fallback)."""
 import json
 import os
+import sys as _sys
+_sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import subprocess
 import sys
 
@@ -26,7 +28,16 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
               "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["value"] > 0 and d["config"]["workload"].startswith("params/forest_best.py")
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the unmodified reference when a checkout is present (build container: /root/reference; GPU box: baseline/_ref),
+    # else the oracle port
+    from oracle.reference_access import find_reference
+    assert d["cpu_baseline"]["kind"] == ("reference" if find_reference() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the driver divides the two arms' values only when unit, steps and warm-up agree: the arm honours its arguments
+    assert d["unit"] == "HVP/s" and d["steps"] == 3 and d["warmup"] == 1
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert re.search(r'^UNIT = "HVP/s"$', src, flags=re.M) and src.count('"unit": UNIT') >= 2
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -6,8 +6,16 @@ import sys
 
 import pytest
 
-REF = os.environ.get("OPTW_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from optwboundeigenval_b200.dropin import find_reference  # noqa: E402
+
+# $OPTW_REFERENCE, /root/reference (build container) or baseline/_ref/optWBoundEigenval (the copy on the GPU box)
+REF = find_reference() or "/nonexistent"
 needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "opt.py")), reason="reference checkout not present")
+
+
+def dropin_saved_iter(opt):
+    return opt._b200_saved["iter"]
 
 
 @needs_ref
@@ -18,12 +26,15 @@ def test_install_patches_and_restores_the_reference_module():
     sys.path.insert(0, REF)
     import opt
     orig_cls_init = opt.OptWBoundEignVal.__init__
+    orig_iter, orig_comp_f = opt.OptWBoundEignVal.iter, opt.OptWBoundEignVal.comp_f
     spec_before = inspect.getfullargspec(opt.OptWBoundEignVal)
     dropin.install(opt)
     try:
         assert opt.HVPOperator is B200HVPOperator
         assert opt.OptWBoundEignVal.comp_rho is spectral.comp_rho
         assert opt.OptWBoundEignVal.comp_gradrho is spectral.comp_gradrho
+        assert opt.OptWBoundEignVal.comp_f is spectral.comp_f
+        assert opt.OptWBoundEignVal.iter is not dropin_saved_iter(opt)
         # opt.missing_params / arg_dic introspect the constructor (opt.py:1940-1965)
         assert inspect.getfullargspec(opt.OptWBoundEignVal) == spec_before
         o = opt.missing_params(opt.OptWBoundEignVal, {"model": None, "loss": None, "optimizer": None})
@@ -31,6 +42,7 @@ def test_install_patches_and_restores_the_reference_module():
     finally:
         dropin.uninstall(opt)
     assert opt.OptWBoundEignVal.__init__ is orig_cls_init
+    assert opt.OptWBoundEignVal.iter is orig_iter and opt.OptWBoundEignVal.comp_f is orig_comp_f
     assert opt.HVPOperator.__name__ == "HVPOperator"
 
 

@@ -424,9 +424,13 @@ def test_fused_step_assembly_matches_iter_body():
     # a full regularised step updates the parameters exactly like torch's SGD on the reference's p
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     before = torch.cat([q.detach().reshape(-1).clone() for q in model.parameters()])
-    pstep = st.regularized_step([x, y], opt)
+    st.regularized_step([x, y], opt)
+    pstep = st.gradf + 0.01 * st.gradg
     after = torch.cat([q.detach().reshape(-1) for q in model.parameters()])
     assert torch.allclose(after, before - 0.1 * pstep.float(), rtol=1e-6, atol=1e-8)
+    # the parameters are now views of one flat vector (what the fused update writes), identity and shapes unchanged
+    from optwboundeigenval_b200.hvp_operator import flat_params_of
+    assert flat_params_of(model, st.device).is_attached()
 
 
 def test_rho_test_sweep_matches_per_batch_comp_rho():
