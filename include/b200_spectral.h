@@ -50,13 +50,15 @@ enum {
     B2S_OP_RELU = 3,     /* standalone ReLU (normally fused into its producer) */
     B2S_OP_MAXPOOL = 4,
     B2S_OP_AVGPOOL = 5,  /* kernel == stride, no padding; adaptive (1,1) maps to kernel = H */
-    B2S_OP_COPY = 6      /* physical copy of a view (fallback for concatenations that cannot alias) */
+    B2S_OP_COPY = 6,     /* physical copy of a view (fallback for concatenations that cannot alias) */
+    B2S_OP_ADD = 7       /* residual connection out = in + tensor[slot] (torchvision Bottleneck, dcnn.py:219-236) */
 };
 
 enum {
     B2S_F_RELU = 1,      /* a ReLU is fused behind this op */
     B2S_F_FIRST = 2,     /* input is network data: no input tangent, no input adjoint */
-    B2S_F_BWD_ACC = 4    /* backward accumulates into the input adjoint instead of overwriting it */
+    B2S_F_BWD_ACC = 4,   /* backward accumulates into the input adjoint instead of overwriting it */
+    B2S_F_BWD_ACC2 = 8   /* B2S_OP_ADD: the same for the second operand's adjoint */
 };
 
 typedef struct {

@@ -49,6 +49,37 @@ __global__ void mask_inplace_kernel(const float* __restrict__ ref, long long rs,
     }
 }
 
+// residual connection y = a + b with an optional fused ReLU: order 0 -> max(a0 + b0, 0), order k -> (y0 > 0) (a_k + b_k)
+__global__ void add_fwd_kernel(int order, int relu, const float* __restrict__ a, long long as, const float* __restrict__ b,
+                               long long bs, const float* __restrict__ y0, long long y0s, float* __restrict__ yk, long long ys,
+                               long long per) {
+    const int n = blockIdx.y;
+    a += n * as; b += n * bs; y0 += n * y0s; yk += n * ys;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x) {
+        float v = a[i] + b[i];
+        if (relu) v = order == 0 ? fmaxf(v, 0.f) : (y0[i] > 0.f ? v : 0.f);
+        yk[i] = v;
+    }
+}
+
+// both operand adjoints (+)= (y0 > 0) g ; a NULL target is skipped (network data has no adjoint)
+__global__ void add_bwd_kernel(const float* __restrict__ y0, long long y0s, const float* __restrict__ g, long long gs,
+                               float* __restrict__ ga, long long gas, int acc_a, float* __restrict__ gb, long long gbs, int acc_b,
+                               long long per) {
+    const int n = blockIdx.y;
+    if (y0) y0 += n * y0s;
+    g += n * gs;
+    if (ga) ga += n * gas;
+    if (gb) gb += n * gbs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = (!y0 || y0[i] > 0.f) ? g[i] : 0.f;
+        if (ga) ga[i] = acc_a ? ga[i] + v : v;
+        if (gb) gb[i] = acc_b ? gb[i] + v : v;
+    }
+}
+
 // order 0: scan the window in (ky,kx) order, first maximum wins (ATen max_pool2d), padding = -inf;
 // order>0: y_k = x_k[argmax]
 __global__ void maxpool_fwd_kernel(int order, const float* __restrict__ x, long long xs, float* __restrict__ y,
@@ -277,6 +308,25 @@ int launch_sub_cast_f32_f64(cudaStream_t st, const float* a, const float* b, dou
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     if (blocks < 1) blocks = 1;
     sub_cast_kernel<<<blocks, 256, 0, st>>>(a, b, out, n);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_add_fwd(cudaStream_t st, int order, int relu, const View& a, const View& b, const View& y0, const View& yk, int batch) {
+    const long long per = (long long)a.C * a.H * a.W;
+    ProfScope prof("add_fwd", (double)per * batch, 12.0 * per * batch, st);
+    add_fwd_kernel<<<ew_grid(per, batch), 256, 0, st>>>(order, relu, a.p, a.sstride, b.p, b.sstride, y0.p, y0.sstride, yk.p,
+                                                      yk.sstride, per);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_add_bwd(cudaStream_t st, const View* y0, const View& g, const View* ga, int acc_a, const View* gb, int acc_b, int batch) {
+    const long long per = (long long)g.C * g.H * g.W;
+    ProfScope prof("add_bwd", (double)per * batch, 16.0 * per * batch, st);
+    add_bwd_kernel<<<ew_grid(per, batch), 256, 0, st>>>(y0 ? y0->p : nullptr, y0 ? y0->sstride : 0, g.p, g.sstride,
+                                                      ga ? ga->p : nullptr, ga ? ga->sstride : 0, acc_a,
+                                                      gb ? gb->p : nullptr, gb ? gb->sstride : 0, acc_b, per);
     B2S_LAUNCH_CHECK();
     return 0;
 }

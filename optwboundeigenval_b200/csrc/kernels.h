@@ -55,6 +55,10 @@ int launch_avgpool_bwd(cudaStream_t st, const View& adj_out, const View& adj_in,
                        int accumulate);
 int launch_copy_view(cudaStream_t st, const View& src, const View& dst, int batch, int accumulate);
 int launch_zero_view(cudaStream_t st, const View& v, int batch);
+// residual connection (B2S_OP_ADD): y_k = a_k + b_k with an optional fused ReLU decided on order 0
+int launch_add_fwd(cudaStream_t st, int order, int relu, const View& a, const View& b, const View& y0, const View& yk, int batch);
+int launch_add_bwd(cudaStream_t st, const View* y0_or_null, const View& g, const View* ga, int acc_a, const View* gb, int acc_b,
+                   int batch);
 int launch_cast_f64_f32(cudaStream_t st, const double* in, float* out, long long n);
 int launch_cast_f32_f64(cudaStream_t st, const float* in, double* out, long long n, double scale);
 

@@ -367,6 +367,10 @@ static int forward(b2s_plan* p, int K, bool eval_mode = false) {
         case B2S_OP_COPY:
             B2S_TRY(launch_copy_view(st, tview(p, p->fw, K, op.in), tview(p, p->fw, K, op.out), p->batch, 0));
             break;
+        case B2S_OP_ADD:
+            B2S_TRY(launch_add_fwd(st, K, relu ? 1 : 0, tview(p, p->fw, K, op.in), tview(p, p->fw, K, op.slot),
+                                   tview(p, p->fw, 0, op.out), tview(p, p->fw, K, op.out), p->batch));
+            break;
         default:
             set_error("unknown op kind %d", op.kind);
             return -5;
@@ -413,6 +417,17 @@ static int join_side(b2s_plan* p) {
     p->side_next = 0;
     p->side_used = false;
     return 0;
+}
+
+// adjoint of a residual connection: both operands receive (mask .) the output adjoint of arena order `ord`
+static int add_backward(b2s_plan* p, const b2s_op& op, int ord) {
+    const int in_buf = p->tensors[0].buf;
+    const bool has_a = p->tensors[op.in].buf != in_buf, has_b = p->tensors[op.slot].buf != in_buf;
+    const View y0 = tview(p, p->fw, 0, op.out), g = tview(p, p->bw, ord, op.out);
+    const View ga = tview(p, p->bw, ord, op.in), gb = tview(p, p->bw, ord, op.slot);
+    return launch_add_bwd(p->stream, (op.flags & B2S_F_RELU) ? &y0 : nullptr, g, has_a ? &ga : nullptr,
+                          (op.flags & B2S_F_BWD_ACC) ? 1 : 0, has_b ? &gb : nullptr, (op.flags & B2S_F_BWD_ACC2) ? 1 : 0,
+                          p->batch);
 }
 
 // ---- backward sweep of order K ----------------------------------------------------------------
@@ -494,6 +509,9 @@ static int backward(b2s_plan* p, int K) {
             if (!first)
                 B2S_TRY(launch_copy_view(st, tview(p, p->bw, K, op.out), tview(p, p->bw, K, op.in), p->batch, acc));
             break;
+        case B2S_OP_ADD:
+            B2S_TRY(add_backward(p, op, K));
+            break;
         default:
             set_error("unknown op kind %d", op.kind);
             return -5;
@@ -568,6 +586,9 @@ static int backward_correction(b2s_plan* p) {
         case B2S_OP_COPY:
             if (!first)
                 B2S_TRY(launch_copy_view(st, tview(p, p->bw, 2, op.out), tview(p, p->bw, 2, op.in), p->batch, acc));
+            break;
+        case B2S_OP_ADD:
+            B2S_TRY(add_backward(p, op, 2));
             break;
         default:
             set_error("unknown op kind %d", op.kind);
@@ -793,6 +814,11 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
         const b2s_op& op = ops[i];
         if (op.in < 0 || op.in >= n_tensors || op.out < 0 || op.out >= n_tensors) {
             set_error("b2s_plan_create: op %d references an unknown tensor", i);
+            delete p;
+            return -1;
+        }
+        if (op.kind == B2S_OP_ADD && (op.slot < 0 || op.slot >= n_tensors)) {
+            set_error("b2s_plan_create: op %d (add) references an unknown second operand", i);
             delete p;
             return -1;
         }

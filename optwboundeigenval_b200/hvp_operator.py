@@ -293,6 +293,9 @@ def set_data_parallel(on: bool):
 
 
 def plan_for(model, criterion, x: torch.Tensor, device, max_batch=None) -> SpectralPlan:
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:        # the reference says torch.device('cuda') (opt.py:247)
+        device = torch.device("cuda", torch.cuda.current_device())
     shape = tuple(x.shape[1:])
     key = (id(model), criterion.__class__.__name__, shape)
     entry = _PLANS.get(key)

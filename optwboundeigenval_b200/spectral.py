@@ -274,14 +274,15 @@ class _FusedOptimizer(object):
         for g, _, ks in self.groups:
             for k in ks:
                 q = self.flat.params[k]
-                e = st[q]
                 if self.kind == 1:
-                    if e.get("momentum_buffer") is not None:
+                    e = st.get(q)                      # plain SGD keeps no state: do not create entries
+                    if e is not None and e.get("momentum_buffer") is not None:
                         v = self._view(self.s1, k)
                         if e["momentum_buffer"].data_ptr() != v.data_ptr():
                             v.copy_(e["momentum_buffer"])
                         e["momentum_buffer"] = v
                 else:
+                    e = st[q]
                     if "step" not in e:
                         e["step"] = torch.tensor(0.0, dtype=torch.float32)
                     for key, buf in (("exp_avg", self.s1), ("exp_avg_sq", self.s2)):
@@ -306,7 +307,7 @@ class _FusedOptimizer(object):
             o.lr, o.weight_decay = float(g["lr"]), float(g["weight_decay"])
             if self.kind == 1:
                 o.momentum, o.dampening, o.nesterov = float(g["momentum"]), float(g["dampening"]), 1 if g["nesterov"] else 0
-                have = [st[self.flat.params[k]].get("momentum_buffer") is not None for k in ks]
+                have = [(st.get(self.flat.params[k]) or {}).get("momentum_buffer") is not None for k in ks]
                 if o.momentum != 0 and any(have) != all(have):
                     raise RuntimeError("fused SGD step: only some parameters of a group have a momentum buffer")
                 o.first_step = 0 if (o.momentum == 0 or all(have)) else 1

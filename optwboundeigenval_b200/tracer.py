@@ -31,8 +31,8 @@ import torch.fx as fx
 import torch.nn as nn
 import torch.nn.functional as F
 
-OP_CONV, OP_BN, OP_RELU, OP_MAXPOOL, OP_AVGPOOL, OP_COPY = 1, 2, 3, 4, 5, 6
-F_RELU, F_FIRST, F_BWD_ACC = 1, 2, 4
+OP_CONV, OP_BN, OP_RELU, OP_MAXPOOL, OP_AVGPOOL, OP_COPY, OP_ADD = 1, 2, 3, 4, 5, 6, 7
+F_RELU, F_FIRST, F_BWD_ACC, F_BWD_ACC2 = 1, 2, 4, 8
 HEAD_CE, HEAD_SOFTMAX_CE, HEAD_WBCE, HEAD_SIGMOID_WBCE = 1, 2, 3, 4
 
 
@@ -83,6 +83,7 @@ class VOp:
     momentum: float = 0.0
     name: str = ""
     module: Optional[nn.Module] = None
+    inp2: int = -1                       # OP_ADD: the second operand
 
 
 @dataclass
@@ -109,13 +110,13 @@ class Tape:
         arr = (COp * len(self.ops))()
         for i, o in enumerate(self.ops):
             kh, kw, sh, sw, ph, pw = o.geom
-            arr[i] = COp(o.kind, o.flags, o.inp, o.out, o.w_off, o.b_off, kh, kw, sh, sw, ph, pw, o.slot,
-                         o.eps, o.momentum)
+            arr[i] = COp(o.kind, o.flags, o.inp, o.out, o.w_off, o.b_off, kh, kw, sh, sw, ph, pw,
+                         o.inp2 if o.kind == OP_ADD else o.slot, o.eps, o.momentum)
         return arr
 
     def describe(self) -> str:
         names = {OP_CONV: "conv", OP_BN: "bn", OP_RELU: "relu", OP_MAXPOOL: "maxpool", OP_AVGPOOL: "avgpool",
-                 OP_COPY: "copy"}
+                 OP_COPY: "copy", OP_ADD: "add"}
         lines = []
         for i, o in enumerate(self.ops):
             ti, to = self.tensors[o.inp], self.tensors[o.out]
@@ -198,13 +199,14 @@ class _Builder:
                            b_off=self.poff[id(m.bias)] if m.bias is not None else -1,
                            geom=(kh, kw, sh, sw, ph, pw), name=name, module=m)
 
-    def linear(self, t, m: nn.Linear, name):
+    def linear(self, t, m, name):
         c, h, w = self.vts[t].shape
-        if c * h * w != m.in_features:
-            raise UnsupportedModel("%s: expected %d features, got %r" % (name, m.in_features, (c, h, w)))
+        n_out, n_in = m._parameters["weight"].shape   # nn.Linear and dnet._linear (dnet.py:105-143, LinearFunction) alike
+        if c * h * w != n_in:
+            raise UnsupportedModel("%s: expected %d features, got %r" % (name, n_in, (c, h, w)))
         if (h, w) != (1, 1):
             t = self.reshape(t, (c * h * w, 1, 1))
-        return self.add_op(OP_CONV, t, (m.out_features, 1, 1), w_off=self.poff[id(m.weight)],
+        return self.add_op(OP_CONV, t, (n_out, 1, 1), w_off=self.poff[id(m.weight)],
                            b_off=self.poff[id(m.bias)] if m.bias is not None else -1, name=name, module=m)
 
     def bn(self, t, m, name):
@@ -241,6 +243,15 @@ class _Builder:
         c, h, w = self.vts[t].shape
         return self.add_op(OP_AVGPOOL, t, (c, h // kh, w // kw), geom=(kh, kw, kh, kw, 0, 0), name=name)
 
+    def add(self, t1, t2, name):
+        """residual connection (torchvision Bottleneck: ``out += identity``, dcnn.py:222-225 MyResNet50)"""
+        if self.vts[t1].shape != self.vts[t2].shape:
+            raise UnsupportedModel("%s: element-wise add of tensors with different shapes %r / %r (no broadcasting)" % (
+                name, self.vts[t1].shape, self.vts[t2].shape))
+        out = self.add_op(OP_ADD, t1, self.vts[t1].shape, name=name, inp2=t2)
+        self.vts[self.root(t2)].users += 1
+        return out
+
     def reshape(self, t, shape):
         if self.vts[t].numel != shape[0] * shape[1] * shape[2]:
             raise UnsupportedModel("reshape changes the per-sample element count: %r -> %r" % (self.vts[t].shape, shape))
@@ -263,11 +274,32 @@ def _is_fn(target, *cands):
     return any(target is c for c in cands)
 
 
+def _custom_function_kind(m: nn.Module) -> Optional[str]:
+    """dnet.py wraps two hand-written autograd Functions in modules: ``_relu`` (MyReLU, dnet.py:30-60) and ``_linear``
+    (LinearFunction, dnet.py:64-143).  Their backward passes are written with differentiable tensor ops, so nested
+    autograd differentiates them like the built-in layers: ``_linear`` is exactly ``nn.Linear``; ``MyReLU`` is ReLU
+    except that its gradient passes where the input is exactly 0.0 (``grad_input[input < 0] = 0``), a set that is
+    empty for floating-point pre-activations of BatchNorm outputs -- it is lowered to the same mask kernels."""
+    name = m.__class__.__name__
+    params = m.__dict__.get("_parameters", {})        # not getattr: fx turns parameter access into proxies while tracing
+    if name == "_relu" and "f" in m.__dict__ and not params:
+        return "relu"
+    if name == "_linear" and params.get("weight") is not None and params["weight"].dim() == 2:
+        return "linear"
+    return None
+
+
+class _Tracer(fx.Tracer):
+    def is_leaf_module(self, m, qualname):
+        return _custom_function_kind(m) is not None or super().is_leaf_module(m, qualname)
+
+
 def trace(model: nn.Module, criterion, input_shape) -> Tape:
     """Lower ``model`` (+ its loss) to a tape. ``input_shape`` is the per-sample input shape."""
     was_training = model.training
     try:
-        gm = fx.symbolic_trace(model)
+        graph = _Tracer().trace(model)
+        gm = fx.GraphModule(model, graph)
     except Exception as exc:   # noqa: BLE001
         raise UnsupportedModel("torch.fx could not trace %s: %s" % (model.__class__.__name__, exc)) from exc
     finally:
@@ -314,6 +346,10 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
                 env[node] = b.bn(t, m, node.target)
             elif isinstance(m, nn.ReLU):
                 env[node] = b.relu(t, node.target, m.inplace)
+            elif _custom_function_kind(m) == "relu":
+                env[node] = b.relu(t, node.target, False)
+            elif _custom_function_kind(m) == "linear":
+                env[node] = b.linear(t, m, node.target)
             elif isinstance(m, nn.MaxPool2d):
                 env[node] = b.maxpool(t, m.kernel_size, m.stride, m.padding, node.target, m.dilation, m.ceil_mode,
                                       m.return_indices)
@@ -348,6 +384,9 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
             tg = node.target
             if _is_fn(tg, torch.relu, F.relu, torch.relu_, F.relu_):
                 env[node] = b.relu(tin(node.args[0]), nm, bool(arg(1, "inplace", False)) or tg in (torch.relu_, F.relu_))
+            elif _is_fn(tg, operator.add, operator.iadd, torch.add) and len(node.args) == 2 \
+                    and all(isinstance(a, fx.Node) and isinstance(env.get(a), int) for a in node.args) and not node.kwargs:
+                env[node] = b.add(tin(node.args[0]), tin(node.args[1]), nm)
             elif _is_fn(tg, torch.cat, torch.concat):
                 dim = arg(1, "dim", 0)
                 if dim != 1:
@@ -410,6 +449,9 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
                 env[node] = b.relu(tin(t0), nm, node.target == "relu_")
             elif node.target == "contiguous":
                 env[node] = tin(t0)
+            elif node.target in ("add", "add_") and len(node.args) == 2 and isinstance(node.args[1], fx.Node) \
+                    and isinstance(env.get(node.args[1]), int) and not node.kwargs:
+                env[node] = b.add(tin(t0), tin(node.args[1]), nm)
             else:
                 raise UnsupportedModel("tensor method .%s() (node %s) has no B200 kernel" % (node.target, nm))
         elif node.op == "get_attr":
@@ -479,6 +521,9 @@ def _finish(b: _Builder, result: int, head: int, input_shape) -> Tape:
     for op in vops:
         r = b.root(op.inp)
         consumers[r] = consumers.get(r, 0) + 1
+        if op.inp2 >= 0:
+            r = b.root(op.inp2)
+            consumers[r] = consumers.get(r, 0) + 1
     for out, ins in b.cats:
         for t in ins:
             r = b.root(t)
@@ -499,7 +544,7 @@ def _finish(b: _Builder, result: int, head: int, input_shape) -> Tape:
                 raise UnsupportedModel("%s: in-place ReLU on a tensor that has other consumers" % op.name)
             continue
         p = vops[prod]
-        if p.kind in (OP_CONV, OP_BN) and not (p.flags & F_RELU):
+        if p.kind in (OP_CONV, OP_BN, OP_ADD) and not (p.flags & F_RELU):
             p.flags |= F_RELU
             keep[i] = False
             replaced[op.out] = src
@@ -511,6 +556,8 @@ def _finish(b: _Builder, result: int, head: int, input_shape) -> Tape:
 
     for op in vops:
         op.inp = resolve(op.inp)
+        if op.inp2 >= 0:
+            op.inp2 = resolve(op.inp2)
     for vt in vts:
         if vt.alias_of is not None:
             vt.alias_of = resolve(vt.alias_of)
@@ -579,6 +626,8 @@ def _finish(b: _Builder, result: int, head: int, input_shape) -> Tape:
     place(0)
     for op in ops:
         place(op.inp)
+        if op.inp2 >= 0:
+            place(op.inp2)
         place(op.out)
     place(result)
     for t in range(len(vts)):
@@ -614,19 +663,20 @@ def _finish(b: _Builder, result: int, head: int, input_shape) -> Tape:
     lg = vts[result]
     written.setdefault(lg.buf, []).append((lg.offset, lg.offset + lg.numel))     # the head writes the logits adjoint
     for op in reversed(ops):
-        if op.flags & F_FIRST:
-            continue
-        vt = vts[op.inp]
-        lo, hi = vt.offset, vt.offset + vt.numel
-        ivs = written.setdefault(vt.buf, [])
-        covered = _covered(ivs, lo, hi)
-        if covered == "none":
-            ivs.append((lo, hi))
-        elif covered == "all":
-            op.flags |= F_BWD_ACC
-        else:
-            raise UnsupportedModel("%s: input adjoint region is partially written by later ops; "
-                                   "this fan-out pattern is not supported" % op.name)
+        for operand, flag in ((op.inp, F_BWD_ACC), (op.inp2, F_BWD_ACC2)):
+            if operand < 0 or vts[operand].buf == in_buf:      # network data has no adjoint
+                continue
+            vt = vts[operand]
+            lo, hi = vt.offset, vt.offset + vt.numel
+            ivs = written.setdefault(vt.buf, [])
+            covered = _covered(ivs, lo, hi)
+            if covered == "none":
+                ivs.append((lo, hi))
+            elif covered == "all":
+                op.flags |= flag
+            else:
+                raise UnsupportedModel("%s: input adjoint region is partially written by later ops; "
+                                       "this fan-out pattern is not supported" % op.name)
     # every op output adjoint must have been written by someone (its consumers) before the op runs backward:
     # guaranteed by topological order as long as each tensor has at least one consumer.
 

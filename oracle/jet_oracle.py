@@ -110,6 +110,9 @@ class JetTapeOracle:
         self.masks = {}
         self.preact = {}
         self.mask_override = {}
+        # the same for max pooling: op index -> int64 index tensor (as F.max_pool2d returns) substituted for the natural
+        # arg-max where two window elements are within fp32 rounding of each other
+        self.argmax_override = {}
         t0 = tape.tensors[0]
         self.view(self.fw, 0, 0).copy_(x.to(DT).reshape(self.B, *t0.shape))
 
@@ -179,6 +182,9 @@ class JetTapeOracle:
                 kh, kw, sh, sw, ph, pw = op.geom
                 if K == 0:
                     y, idx = F.max_pool2d(xin[0], (kh, kw), (sh, sw), (ph, pw), return_indices=True)
+                    if oi in self.argmax_override:
+                        idx = self.argmax_override[oi]
+                        y = xin[0].flatten(2).gather(2, idx.flatten(2)).view_as(y)
                     self.argmax[oi] = idx
                     yout.copy_(y)
                 else:
@@ -189,6 +195,11 @@ class JetTapeOracle:
                 yout.copy_(F.avg_pool2d(xin[K], op.geom[0]))
             elif op.kind == T.OP_COPY:
                 yout.copy_(xin[K])
+            elif op.kind == T.OP_ADD:
+                y = xin[K] + self.view(self.fw, K, op.inp2)
+                if relu:
+                    y = self.decide(oi, y) if K == 0 else y * self.masks[oi]
+                yout.copy_(y)
             else:
                 raise RuntimeError("op kind %d" % op.kind)
         self.head(K)
@@ -362,6 +373,19 @@ class JetTapeOracle:
             elif op.kind == T.OP_COPY:
                 if not first:
                     emit(g[K])
+            elif op.kind == T.OP_ADD:
+                val = g[K] * self.masks[oi] if relu else g[K]
+                if not first:
+                    emit(val)
+                self._emit2(self.view(self.bw, K, op.inp2), op, val)
+
+    def _emit2(self, xbar2, op, val):
+        if self.tape.tensors[op.inp2].buf == self.tape.tensors[0].buf:
+            return
+        if op.flags & T.F_BWD_ACC2:
+            xbar2.add_(val)
+        else:
+            xbar2.copy_(val)
 
     # ---- reference-compatible third order through BatchNorm -------------------------------------
     def bn_third_order_defect(self):
@@ -460,6 +484,11 @@ class JetTapeOracle:
             elif op.kind == T.OP_COPY:
                 if not first:
                     emit(g)
+            elif op.kind == T.OP_ADD:
+                val = g * self.masks[oi] if relu else g
+                if not first:
+                    emit(val)
+                self._emit2(cview(op.inp2), op, val)
         return out
 
     def vghv(self, v, mode="reference"):

@@ -8,6 +8,9 @@ such an element differently, and ONE flipped decision moves the gradient by more
 north star asks for (the reference's own fp32 result is that far from an fp64 evaluation of itself,
 tests/test_gpu_parity.py::test_full_size_chest_models_against_cpu_autograd).
 
+Max pooling is piecewise linear too: a window whose two largest elements differ by less than fp32 rounding may route
+its adjoint to either element.
+
 `explain_by_kinks` makes that statement checkable instead of loosening the tolerance:
   1. the fp64 jet oracle (oracle/jet_oracle.py, pinned to nested autograd by tests/test_jet_oracle.py)
      evaluates the same tape; every ReLU decision the GPU took differently must sit on a pre-activation
@@ -40,6 +43,19 @@ def gpu_relu_decisions(plan, batch):
     for oi, op in enumerate(plan.tape.ops):
         if op.kind == tracer.OP_RELU or (op.flags & tracer.F_RELU):
             out[oi] = torch.from_numpy(_read_value(plan, op.out, batch) > 0)
+    return out
+
+
+def gpu_argmax_decisions(plan, batch):
+    """op index -> the window element every max pool of the cached base pass selected, recomputed from the GPU's own
+    fp32 input values with the same first-maximum rule (elementwise.cu maxpool_fwd_kernel / ATen)"""
+    import torch.nn.functional as F
+    out = {}
+    for oi, op in enumerate(plan.tape.ops):
+        if op.kind == tracer.OP_MAXPOOL:
+            kh, kw, sh, sw, ph, pw = op.geom
+            xin = torch.from_numpy(_read_value(plan, op.inp, batch))
+            out[oi] = F.max_pool2d(xin, (kh, kw), (sh, sw), (ph, pw), return_indices=True)[1]
     return out
 
 
@@ -77,8 +93,26 @@ def explain_by_kinks(op, model, x, y, checks, rtol=1e-4, kink_tol=1e-5, max_flip
                 "tensor rms %.3e" % (oi, plan.tape.ops[oi].name, worst, scale))
             flips += n
     assert flips <= max(1, int(max_flip_fraction * total)), "%d of %d ReLU decisions differ" % (flips, total)
+    # max pooling is the other piecewise-linear op: a window whose two largest elements are within fp32 rounding of each
+    # other may route its adjoint to either of them
+    argmax = gpu_argmax_decisions(plan, batch)
+    for oi, idx_gpu in argmax.items():
+        idx_ref = nat.argmax[oi]
+        d = idx_gpu != idx_ref
+        n = int(d.sum())
+        if n:
+            xin = nat.view(nat.fw, 0, plan.tape.ops[oi].inp).flatten(2)
+            a = xin.gather(2, idx_gpu.flatten(2)).view_as(d)[d]
+            b = xin.gather(2, idx_ref.flatten(2)).view_as(d)[d]
+            scale = float(xin.pow(2).mean().sqrt())
+            worst = float((a - b).abs().max())
+            assert worst <= kink_tol * scale, (
+                "op %d (%s): a max-pool selection differs where the two candidates are NOT fp32-ambiguous: %.3e apart, "
+                "tensor rms %.3e" % (oi, plan.tape.ops[oi].name, worst, scale))
+            flips += int(((a != 0) | (b != 0)).sum())       # ties among zeros (behind a ReLU) carry no adjoint
     cond = _oracle(plan, model, x, y)
     cond.mask_override = decisions
+    cond.argmax_override = argmax
     grad = cond.run(0)
     for name, kind, v, got in checks:
         if kind == "grad":

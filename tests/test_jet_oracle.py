@@ -173,3 +173,128 @@ def test_exact_third_order_is_the_true_derivative_and_torch_bn_is_not():
     assert rel_err(exact.numpy(), fd.numpy()) < 1e-5
     assert rel_err(compat.numpy(), ref.numpy()) < 1e-10
     assert rel_err(ref.numpy(), fd.numpy()) > 1e-2
+
+
+class _TinyResNet(torch.nn.Module):
+    """torchvision-style bottleneck blocks: identity and strided 1x1 down-sample shortcuts, `out += identity`, one
+    shared in-place ReLU module per block (dcnn.py:219-236 builds MyResNet50 from these)."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        self.conv1 = nn.Conv2d(3, 8, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(8)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        from torchvision.models.resnet import Bottleneck
+        down = nn.Sequential(nn.Conv2d(8, 16, 1, stride=2, bias=False), nn.BatchNorm2d(16))
+        self.layer1 = nn.Sequential(Bottleneck(8, 4, stride=2, downsample=down), Bottleneck(16, 4))
+        self.fc = nn.Linear(16, 5)
+
+    def forward(self, x):
+        h = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        h = self.layer1(h)
+        h = torch.nn.functional.adaptive_avg_pool2d(h, (1, 1))
+        return self.fc(torch.flatten(h, 1))
+
+
+def test_residual_add_jets_match_autograd_fp64():
+    """OP_ADD (residual connections, fused ReLU, two-operand overwrite/accumulate analysis) against nested autograd."""
+    torch.manual_seed(21)
+    model = _TinyResNet().train()
+    loss = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(6, 3, 32, 32, generator=g)
+    y = torch.randint(0, 5, (6,), generator=g)
+    tape = tracer.trace(model, loss, (3, 32, 32))
+    assert sum(1 for o in tape.ops if o.kind == tracer.OP_ADD) == 2
+    assert all(o.flags & tracer.F_RELU for o in tape.ops if o.kind == tracer.OP_ADD)
+    model64 = model.double()
+    op = ao.AutogradSpectralOperator(model64, [x.double(), y], loss)
+    P = tape.n_params
+    v = torch.randn(P, generator=g, dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    jo = JetTapeOracle(tape, ao.flat_params(model64), x, y)
+    assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 1e-10
+    assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 1e-9
+    assert rel_err(jo.vghv(v).numpy(), op.vghv(v).numpy()) < 1e-8
+
+
+def test_dnet_custom_function_modules_lower_to_relu_and_linear():
+    """dnet.py's hand-written autograd Functions (MyReLU dnet.py:30-60, LinearFunction dnet.py:64-99) behind the
+    `_relu` / `_linear` modules: same tape as the built-in layers, same jets as nested autograd through the custom
+    backward passes (restated here; the reference's own classes are traced in tests/test_dropin.py)."""
+    class MyReLU(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, inp):
+            ctx.save_for_backward(inp)
+            return inp.clamp(min=0)
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            inp, = ctx.saved_tensors
+            gi = grad_output.clone()
+            gi[inp < 0] = 0
+            return gi
+
+    class LinearFunction(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, inp, weight, bias=None):
+            ctx.save_for_backward(inp, weight, bias)
+            out = inp.mm(weight.t())
+            if bias is not None:
+                out += bias.unsqueeze(0).expand_as(out)
+            return out
+
+        @staticmethod
+        def backward(ctx, go):
+            inp, weight, bias = ctx.saved_tensors
+            return go.mm(weight), go.t().mm(inp), go.sum(0)
+
+    class _relu(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.f = MyReLU.apply
+
+        def forward(self, x):
+            return self.f(x)
+
+    class _linear(torch.nn.Module):
+        def __init__(self, n_in, n_out):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.empty(n_out, n_in).uniform_(-0.3, 0.3))
+            self.bias = torch.nn.Parameter(torch.empty(n_out).uniform_(-0.1, 0.1))
+
+        def forward(self, x):
+            return LinearFunction.apply(x, self.weight, self.bias)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            nn = torch.nn
+            self.features = nn.Sequential(nn.Conv2d(3, 6, 3, padding=1, bias=False), nn.BatchNorm2d(6), _relu(),
+                                          nn.Conv2d(6, 4, 1, bias=False), nn.BatchNorm2d(4))
+            self.classifier = _linear(4, 3)
+
+        def forward(self, x):
+            h = torch.nn.functional.relu(self.features(x), inplace=True)
+            h = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(h, (1, 1)), 1)
+            return self.classifier(h)
+
+    torch.manual_seed(31)
+    model = Net().train()
+    loss = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(5, 3, 8, 8, generator=g)
+    y = torch.randint(0, 3, (5,), generator=g)
+    tape = tracer.trace(model, loss, (3, 8, 8))
+    kinds = [o.kind for o in tape.ops]
+    assert kinds == [tracer.OP_CONV, tracer.OP_BN, tracer.OP_CONV, tracer.OP_BN, tracer.OP_AVGPOOL, tracer.OP_CONV]
+    model64 = model.double()
+    op = ao.AutogradSpectralOperator(model64, [x.double(), y], loss)
+    v = torch.randn(tape.n_params, generator=g, dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    jo = JetTapeOracle(tape, ao.flat_params(model64), x, y)
+    assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 1e-10
+    assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 1e-9
+    assert rel_err(jo.vghv(v).numpy(), op.vghv(v).numpy()) < 1e-8
