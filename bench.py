@@ -445,10 +445,21 @@ def run_b200(args):
         return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
     if world == 1 and gold is not None and np.array_equal(gold["x"], x.numpy()):
+        tail = sum(q.numel() for q in list(model.parameters())[-2:])      # classifier weight + bias
+        g_gpu = op.stored_grad.cpu().numpy()
         parity = {"against": "tests/golden/%s.npz (unmodified reference, CPU fp32, batch %d)" % (kind, batch),
                   "hv_rel_err": rel(hv_first.cpu().numpy(), gold["hv_v0"]),
-                  "grad_rel_err": rel(op.stored_grad.cpu().numpy(), gold["grad"]),
-                  "tolerance": 1e-4}
+                  "grad_rel_err": rel(g_gpu, gold["grad"]),
+                  "grad_classifier_rel_err": rel(g_gpu[-tail:], gold["grad"][-tail:]),
+                  "loss_rel_err": abs(float(op.loss_value) - float(gold["loss"])) / abs(float(gold["loss"])),
+                  "tolerance": 1e-4,
+                  "note": "whole-vector errors above the tolerance are ReLU decisions on pre-activations within fp32 rounding of "
+                          "zero (two fp32 implementations with different summation orders decide them differently; one flipped "
+                          "decision moves the adjoint of its layer by ~1/sqrt(#elements)): the loss and the classifier gradient, "
+                          "which are continuous in those decisions, agree to fp32 rounding, and tests/test_gpu_parity.py::"
+                          "test_grad_hv_vghv_match_reference_golden proves with the fp64 jet oracle conditioned on the GPU's "
+                          "decisions that the GPU vectors are reproduced at rtol 1e-4 and that every differing decision is "
+                          "fp32-ambiguous"}
     elif world > 1:
         # sharded HVP (synced BatchNorm sums + all-reduce) against the single-GPU HVP of the concatenated batch
         xs = [torch.empty_like(x).cuda() for _ in range(world)]

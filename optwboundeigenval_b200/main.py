@@ -19,7 +19,7 @@ import sys
 import tempfile
 
 
-def run(pfile, reference, offline=False, overrides=None, workdir=None, install=True, n_train=512, n_eval=128):
+def run(pfile, reference, offline=False, overrides=None, workdir=None, install=True, n_train=512, n_eval=128, seed=1226):
     from . import dropin
     reference = os.path.abspath(reference)
     if not os.path.exists(os.path.join(reference, "opt.py")):
@@ -41,6 +41,15 @@ def run(pfile, reference, offline=False, overrides=None, workdir=None, install=T
     os.chdir(workdir)
     try:
         sys.path.insert(0, "./params")
+        if seed is not None:
+            # the parameter files carry 'seed': 1226 but nothing reads it: weights, the shuffling of
+            # the loaders and iter()'s random end-of-epoch minibatch (opt.py:604) are seeded here so that runs repeat
+            import random
+            import numpy as np
+            import torch
+            random.seed(seed)
+            np.random.seed(seed)
+            torch.manual_seed(seed)
         params = __import__(pfile)
         if overrides:
             orig = params.options
@@ -80,8 +89,10 @@ def main(argv=None):
     ap.add_argument("--no-install", action="store_true")
     ap.add_argument("--n-train", type=int, default=512, help="--offline: synthetic training samples")
     ap.add_argument("--n-eval", type=int, default=128, help="--offline: synthetic validation / test samples")
+    ap.add_argument("--seed", type=int, default=1226, help="seed of python / numpy / torch generators (-1: leave unseeded)")
     a = ap.parse_args(argv)
-    wd = run(a.pfile, a.reference, a.offline, _parse_overrides(a.set), a.workdir, not a.no_install, a.n_train, a.n_eval)
+    wd = run(a.pfile, a.reference, a.offline, _parse_overrides(a.set), a.workdir, not a.no_install, a.n_train, a.n_eval,
+             None if a.seed < 0 else a.seed)
     print("logs and models under", wd)
 
 

@@ -90,7 +90,7 @@ def test_comp_rho_and_gradrho_match_reference_golden(name, kind, tmp_path):
         assert abs(st.rho - float(g["rho1_rho"])) <= lam_tol * float(g["rho1_rho"])
     v = st.v.cpu().numpy()
     assert st.v.dtype == torch.float64 and st.v.is_cuda
-    assert min(rel_err(v, g["rho1_v"]), rel_err(-v, g["rho1_v"])) < 1e-3
+    assert min(rel_err(v, g["rho1_v"]), rel_err(-v, g["rho1_v"])) < (1e-3 if lam_tol == RTOL_LAM else 5e-3)
     # per-iteration lambda of the verbose log (opt.py:466)
     rows = [ln.split("\t") for ln in open(tmp_path / "v.log").read().splitlines() if ln and ln[0].isdigit()]
     lam = np.array([float(r[1]) for r in rows])
