@@ -419,6 +419,16 @@ static int join_side(b2s_plan* p) {
     return 0;
 }
 
+// The weight gradient of a layer is a leaf of the sweep: it goes to a side stream right away.  (Measured and dropped in
+// round 2: queueing the leaves of a dense block and contracting them in one persistent launch per block -- 2.65..2.78 ms
+// per HVP against 2.50 ms: the per-layer launches fill the SMs the latency-bound adjoint chain leaves idle, a grouped
+// launch can only start when its block is finished and the largest group ends up exposed at the end of the sweep.)
+static int conv_wgrad_leaf(b2s_plan* p, const ConvGeom& g, int np, const float* const* a_, const float* const* b_,
+                           const float* sc, float* wbar) {
+    B2S_TRY(fork_side(p));
+    return launch_conv_wgrad(p->wgrad_side ? p->side : p->stream, g, np, a_, b_, sc, wbar);
+}
+
 // adjoint of a residual connection: both operands receive (mask .) the output adjoint of arena order `ord`
 static int add_backward(b2s_plan* p, const b2s_op& op, int ord) {
     const int in_buf = p->tensors[0].buf;
@@ -460,12 +470,12 @@ static int backward(b2s_plan* p, int K) {
             a_[np] = x[0]; b_[np] = gk[K]; sc[np] = 1.f; ++np;
             if (!first && K >= 1) { a_[np] = x[1]; b_[np] = gk[K - 1]; sc[np] = K == 2 ? 2.f : 1.f; ++np; }
             if (!first && K == 2) { a_[np] = x[2]; b_[np] = gk[0]; sc[np] = 1.f; ++np; }
-            B2S_TRY(fork_side(p));
-            cudaStream_t ws = p->wgrad_side ? p->side : st;
-            B2S_TRY(launch_conv_wgrad(ws, g, np, a_, b_, sc, p->out32[K] + op.w_off));
-            if (op.b_off >= 0)
-                B2S_TRY(launch_bias_grad(ws, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
+            B2S_TRY(conv_wgrad_leaf(p, g, np, a_, b_, sc, p->out32[K] + op.w_off));
+            if (op.b_off >= 0) {
+                B2S_TRY(fork_side(p));
+                B2S_TRY(launch_bias_grad(p->wgrad_side ? p->side : st, gk[K], p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
                                          p->out32[K] + op.b_off));
+            }
             if (!first) {
                 np = 0;
                 a_[np] = gk[K]; b_[np] = W; sc[np] = 1.f; ++np;
@@ -544,11 +554,12 @@ static int backward_correction(b2s_plan* p) {
             const float* gc = tptr(p, p->bw, 2, op.out);
             const float* W = p->params + op.w_off;
             const float one = 1.f;
-            B2S_TRY(fork_side(p));
-            cudaStream_t ws = p->wgrad_side ? p->side : st;
-            B2S_TRY(launch_conv_wgrad(ws, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
-            if (op.b_off >= 0)
-                B2S_TRY(launch_bias_grad(ws, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride, p->out_corr + op.b_off));
+            B2S_TRY(conv_wgrad_leaf(p, g, 1, &x0, &gc, &one, p->out_corr + op.w_off));
+            if (op.b_off >= 0) {
+                B2S_TRY(fork_side(p));
+                B2S_TRY(launch_bias_grad(p->wgrad_side ? p->side : st, gc, p->batch, g.Cout, g.OH * g.OW, g.out_sstride,
+                                         p->out_corr + op.b_off));
+            }
             if (!first) {
                 const float* pk = tc_image(p, oi, MODE_DGRAD, W);
                 B2S_TRY(launch_conv_dgrad(st, g, 1, &gc, &W, &one, tptr(p, p->bw, 2, op.in), acc, &pk));
