@@ -409,7 +409,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     kind = args.config
     batch = args.batch or zoo.CONFIGS[kind][3]
     warmup = max(args.warmup, 3)
@@ -467,17 +467,20 @@ def run_b200(args):
         dist.all_gather(xs, x.cuda())
         dist.all_gather(ys, y.cuda())
         if rank == 0:
-            hvp_operator.set_data_parallel(False)
-            try:
-                one = B200HVPOperator(model, [torch.cat(xs), torch.cat(ys)], loss)
-                hv_one = one.Hv(v0, storedGrad=True)
-                parity = {"against": "single-GPU HVP of the concatenated %d-image batch" % (batch * world),
-                          "hv_rel_err": rel(hv_first.cpu().numpy(), hv_one.cpu().numpy()),
-                          "grad_rel_err": rel(op.stored_grad.cpu().numpy(), one.stored_grad.cpu().numpy()),
-                          "tolerance": 1e-4}
-                del one
-            finally:
-                hvp_operator._DATA_PARALLEL = True     # keep the sharded plan cached
+            # a plan of its own, outside the per-model cache and without a communicator (the cached sharded plan must stay
+            # the one every rank uses); the BatchNorm running statistics its base pass updates are put back
+            buffers = [t.clone() for t in model.buffers()]
+            one = hvp_operator.SpectralPlan(model, loss, tuple(x.shape[1:]), batch * world, torch.device("cuda", local))
+            g_one, _ = one.base_pass(hvp_operator.flat_parameters(model), torch.cat(xs), torch.cat(ys))
+            hv_one = one.hv(v0)
+            parity = {"against": "single-GPU HVP of the concatenated %d-image batch" % (batch * world),
+                      "hv_rel_err": rel(hv_first.cpu().numpy(), hv_one.cpu().numpy()),
+                      "grad_rel_err": rel(op.stored_grad.cpu().numpy(), g_one.cpu().numpy()),
+                      "tolerance": 1e-4}
+            del one
+            with torch.no_grad():
+                for t, saved in zip(model.buffers(), buffers):
+                    t.copy_(saved)
         barrier()
 
     # ---- device-resident loop -------------------------------------------------------------------
@@ -564,6 +567,28 @@ def run_b200(args):
                    "h2d_bytes_per_step": int(x.numel() * 4 + y.numel() * 8), "rho": float(st.rho)}
         except Exception as e:   # noqa: BLE001  (the headline line must survive a failure of this extra leg)
             reg = {"error": repr(e)}
+
+    # ---- strong scaling: the config's batch as written (32 images) split over the N GPUs -----------------------------
+    strong = None
+    if world > 1 and batch % world == 0:
+        per = batch // world
+        xg, yg = zoo.synthetic_batch(kind, batch)                       # the same global batch on every rank
+        op_s = B200HVPOperator(model, [xg[rank * per:(rank + 1) * per], yg[rank * per:(rank + 1) * per]], loss)
+        op_s.Hv(v0, storedGrad=True)
+        op_s.power_iterate(v0, 0.0, warmup)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        op_s.power_iterate(v0, 0.0, args.steps)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"value": args.steps / (float(ts[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(ts[0]) / args.steps,
+                  "global_batch": batch, "batch_per_gpu": per, "scaling": "strong",
+                  "note": "the minibatch of the config as written split over the GPUs: %d images per GPU, the 78 synced "
+                          "BatchNorm exchanges per HVP dominate (SURVEY 8e)" % per}
+        op.Hv(v0, storedGrad=True)                                      # the weak-scaling shard is the cached base pass again
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -668,6 +693,7 @@ def run_b200(args):
                 "gpu_autograd_yardstick": yard,
                 "per_config": table,
                 "parity": parity or None,
+                "strong_scaling": strong,
                 "kernel_profile_ms": {r["name"]: round(r["ms"], 4) for r in prof},
                 "lambda_max": out.lam}
         sys.stdout.flush()

@@ -56,7 +56,7 @@ static NcclApi* nccl() {
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
-    void* xbuf = nullptr;              // [flags 256 B][2 x kPeerCap doubles]
+    void* xbuf = nullptr;              // [flags][2 parities x kPeerMax sources x kPeerCap doubles] (peer.cuh)
     void* peer_base[kPeerMax] = {};
     unsigned long long* d_seq = nullptr;
     unsigned int* d_ticket = nullptr;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(double* __restrict_
 int comm_peer_local(Comm* c, void* h_handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (!c->xbuf) {
-        const size_t bytes = kPeerFlagBytes + 2 * (size_t)kPeerCap * sizeof(double);
+        const size_t bytes = kPeerBufBytes;
         B2S_CUDA(cudaMalloc(&c->xbuf, bytes));
         B2S_CUDA(cudaMemset(c->xbuf, 0, bytes));
         B2S_CUDA(cudaMalloc(&c->d_seq, sizeof(unsigned long long)));
@@ -167,8 +167,8 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
     }
     PeerCtx& x = c->ctx;
     for (int r = 0; r < c->world; ++r) {
-        x.flag[r] = reinterpret_cast<const unsigned long long*>(c->peer_base[r]);
-        x.data[r] = reinterpret_cast<const double*>(static_cast<char*>(c->peer_base[r]) + kPeerFlagBytes);
+        x.flag[r] = reinterpret_cast<unsigned long long*>(c->peer_base[r]);
+        x.data[r] = reinterpret_cast<double*>(static_cast<char*>(c->peer_base[r]) + kPeerFlagBytes);
     }
     x.own_flag = reinterpret_cast<unsigned long long*>(c->xbuf);
     x.own_data = reinterpret_cast<double*>(static_cast<char*>(c->xbuf) + kPeerFlagBytes);

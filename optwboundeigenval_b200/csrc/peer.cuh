@@ -1,12 +1,17 @@
 // peer.cuh -- one-shot all-reduce of small fp64 vectors over NVLink peer memory, callable from inside a kernel.
 //
-// Every rank owns an exchange buffer [2 sequence flags, 128 B apart][2 slots x kPeerCap doubles] that all peers
-// have mapped with cudaIpc (comm.cu).  peer_exchange_block() is executed by ONE thread block per rank:
-// publish the vector in slot (call number & 1), raise the flag (st.release.sys), poll the peers' flags
-// (ld.acquire.sys through NVSwitch), add the peers' vectors in rank order (bitwise identical on all ranks).
+// Every rank owns an exchange buffer that all peers have mapped with cudaIpc (comm.cu):
+//     flags [2 parities][kPeerMax sources]            (16 B apart)
+//     data  [2 parities][kPeerMax sources][kPeerCap doubles]
+// peer_exchange_block() is executed by ONE thread block per rank and PUSHES: it writes its vector into slot
+// (parity, own rank) of EVERY rank's buffer (posted stores through NVSwitch, nothing waits for them), fences, raises
+// flag (parity, own rank) in every buffer (st.release.sys), then polls the flags of its OWN buffer -- local memory --
+// and sums the slots in rank order (bitwise identical on all ranks).  The round-1 form published locally and pulled:
+// every poll of a remote flag and every load of remote data was an NVLink round trip on the critical path of the
+// BatchNorm layer that waits for the sums.
+// A rank can be at most one call ahead of a peer -- it needs the peer's flag of the previous call to get there -- so
+// two parities are enough and no slot is overwritten while a peer still reads it.
 // A peer that does not arrive within B2S_PEER_TIMEOUT_S seconds (default 600) sets a host-visible error flag.
-// A rank can be at most one call ahead of a peer -- it needs the peer's flag of the previous call to get
-// there -- so two slots are enough and no slot is overwritten while a peer still reads it.
 // The BatchNorm kernels call it between their statistics and apply phases (bn.cu), which makes the per-layer
 // statistics all-reduce part of the kernel that produces and consumes the sums instead of a separate
 // NCCL launch between two kernels.
@@ -17,11 +22,12 @@ namespace b2s {
 
 constexpr int kPeerMax = 8;            // GPUs of one box
 constexpr int kPeerCap = 4096;         // doubles per slot
-constexpr int kPeerFlagBytes = 256;    // two 8-byte sequence flags, 128 bytes apart
+constexpr int kPeerFlagBytes = 2 * kPeerMax * 16;     // [parity][source] 8-byte sequence flags, 16 bytes apart
+constexpr size_t kPeerBufBytes = kPeerFlagBytes + 2 * (size_t)kPeerMax * kPeerCap * sizeof(double);
 
 struct PeerCtx {
-    const double* data[kPeerMax];      // every rank's exchange data (own = local pointer), [2 slots][kPeerCap]
-    const unsigned long long* flag[kPeerMax];
+    double* data[kPeerMax];            // every rank's exchange data (own = local pointer), [2][kPeerMax][kPeerCap]
+    unsigned long long* flag[kPeerMax];    // every rank's flags, [2][kPeerMax] (stride 2 words)
     double* own_data;
     unsigned long long* own_flag;
     unsigned long long* seq;           // device-resident call counter (graph replays advance it)
@@ -50,18 +56,21 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 __device__ __forceinline__ void peer_exchange_block(double* buf, const int n, const PeerCtx& ctx) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x, nth = blockDim.x * blockDim.y;
     const unsigned long long seq = *((volatile unsigned long long*)ctx.seq) + 1;
-    const int slot = (int)(seq & 1);
-    double* mine = ctx.own_data + (size_t)slot * kPeerCap;
-    for (int i = tid; i < n; i += nth) mine[i] = __ldcg(buf + i);
+    const int par = (int)(seq & 1);
+    const size_t slot = ((size_t)par * kPeerMax + ctx.rank) * kPeerCap;          // where MY vector goes in every buffer
+    for (int i = tid; i < n; i += nth) {
+        const double v = __ldcg(buf + i);
+        for (int r = 0; r < ctx.world; ++r) ctx.data[r][slot + i] = v;             // own buffer and every peer's
+    }
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) st_release_sys(ctx.own_flag + slot * 16, seq);
+    if (tid < ctx.world) st_release_sys(ctx.flag[tid] + (par * kPeerMax + ctx.rank) * 2, seq);
     if (tid < ctx.world && tid != ctx.rank) {
-        const unsigned long long* f = ctx.flag[tid] + slot * 16;
         // a peer that is merely late (graph instantiation, lazy module load, a stalled data loader) is waited for;
         // one that never arrives within the (wall-clock, configurable) limit raises the host-visible error flag and
         // the exchange returns with an incomplete sum -- the host reports it at the end of the call (plan.cu leave()),
         // the context stays usable (no trap)
+        const unsigned long long* f = ctx.own_flag + (par * kPeerMax + tid) * 2;      // local memory
         unsigned long long t0 = 0;
         unsigned int spins = 0;
         while (ld_acquire_sys(f) < seq) {
@@ -73,9 +82,10 @@ __device__ __forceinline__ void peer_exchange_block(double* buf, const int n, co
         }
     }
     __syncthreads();
+    const double* mine = ctx.own_data + (size_t)par * kPeerMax * kPeerCap;
     for (int i = tid; i < n; i += nth) {
         double s = 0.0;
-        for (int r = 0; r < ctx.world; ++r) s += __ldcv(ctx.data[r] + (size_t)slot * kPeerCap + i);
+        for (int r = 0; r < ctx.world; ++r) s += __ldcv(mine + (size_t)r * kPeerCap + i);
         buf[i] = s;
     }
     __threadfence();

@@ -1366,7 +1366,9 @@ static int power_loop_polled(b2s_plan* p, b2s_pistate* s, int max_iter) {
     }
     int lag = p->poll_lag;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    if (lag < 0) {
+    if (p->comm) {
+        lag = 0;       // data parallel: every rank must enqueue the same number of passes (they contain collectives)
+    } else if (lag < 0) {
         if (const char* e = getenv("B2S_POLL_LAG")) p->poll_lag = std::max(0, std::min((int)b2s_plan::kMaxLag, atoi(e)));
         lag = 0;                                   // first call: synchronous, and the first iteration is timed
         if (p->poll_lag < 0) {
