@@ -14,6 +14,7 @@
 // single-pass TF32).  GEMM view:
 //   forward / dgrad:  M = destination channels, N = batch*pixels, K = source channels*KH*KW
 //   wgrad:            M = Cout, N = Cin*KH*KW, K = batch*pixels (split across blockIdx.z)
+#include <algorithm>
 #include "conv_args.h"
 #include "kernels.h"
 
@@ -504,18 +505,25 @@ conv_wgrad_kernel(const ConvKArgs a) {
     }
 }
 
-// bbar[c] += sum over (n, pix) of adj
+// bbar[c] += sum over (n, pix) of adj.  grid = (C, samples, chunks of a plane): contiguous 128-bit loads of one
+// (sample, channel) plane slice per block, no integer division per element (round 1: a 64-bit division per element
+// made the 15 launches of VGG16 cost 5.5 ms per HVP).
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ adj, int batch, int C, int HW,
                                                         long long sstride, float* __restrict__ bbar) {
     __shared__ float red[32];
     const int c = blockIdx.x;
-    const long long total = (long long)batch * HW;
     float s = 0.f;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.y * blockDim.x) {
-        const int n = (int)(i / HW);
-        const int pix = (int)(i - (long long)n * HW);
-        s += adj[(long long)n * sstride + (long long)c * HW + pix];
+    for (int n = blockIdx.y; n < batch; n += gridDim.y) {
+        const float* __restrict__ p = adj + (long long)n * sstride + (long long)c * HW;
+        if (((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+            for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < (HW >> 2); i += gridDim.z * blockDim.x) {
+                const float4 v = __ldg(p4 + i);
+                s += (v.x + v.y) + (v.z + v.w);
+            }
+        } else {
+            for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < HW; i += gridDim.z * blockDim.x) s += __ldg(p + i);
+        }
     }
     float v[1] = {s};
     block_sum<1, float>(v, red);
@@ -641,13 +649,13 @@ int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const floa
 
 int launch_bias_grad(cudaStream_t st, const float* adj, int batch, int C, int HW, long long sstride,
                      float* bbar) {
-    const long long total = (long long)batch * HW;
-    int splits = (int)((total + 256 * 8 - 1) / (256 * 8));
-    const int cap = (4 * kNumSMs + C - 1) / C;
-    if (splits > cap) splits = cap;
-    if (splits < 1) splits = 1;
+    // about 4 blocks per SM: samples first, then chunks of a plane (each thread should still see >= 8 float4)
+    const int cap = std::max(1, (4 * kNumSMs + C - 1) / C);
+    const int ny = std::min(batch, cap);
+    int nz = std::min(std::max(1, cap / ny), std::max(1, HW / (256 * 4 * 8)));
+    if (nz > 64) nz = 64;
     ProfScope prof("bias_grad", (double)batch * C * HW, 4.0 * batch * C * HW, st);
-    dim3 grid(C, splits);
+    dim3 grid(C, ny, nz);
     bias_grad_kernel<<<grid, 256, 0, st>>>(adj, batch, C, HW, sstride, bbar);
     B2S_LAUNCH_CHECK();
     return 0;

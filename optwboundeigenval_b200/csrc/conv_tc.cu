@@ -584,8 +584,7 @@ int try_launch_conv_tc(int mode, cudaStream_t st, const ConvKArgs& a) {
     const long long J = (long long)g.batch * (mode == MODE_FWD ? g.OH * g.OW : g.H * g.W);
     // automatic: enough pixel tiles to be worth a tensor-core launch; classifier-sized problems stay on the
     // CUDA-core kernels
-    (void)Cs;
-    if (g_tc_mode == 1 && J < 1024) return 0;
+    if (g_tc_mode == 1 && !tc_worth_it(J, Cs, Cd, g.KH * g.KW)) return 0;
     return mode == MODE_FWD ? launch_tc_mode<MODE_FWD>(st, a, J, Cd) : launch_tc_mode<MODE_DGRAD>(st, a, J, Cd);
 }
 

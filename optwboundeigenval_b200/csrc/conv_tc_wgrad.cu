@@ -371,7 +371,7 @@ int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a0) {
     for (int p = 0; p < a.npairs; ++p)
         if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) return 0;
     if (J >= (1LL << 31) || (long long)g.Cin * g.H * g.W >= (1LL << 31) || (long long)g.Cout * g.OH * g.OW >= (1LL << 31)) return 0;
-    if (mode == 1 && J < 1024) return 0;
+    if (mode == 1 && !tc_worth_it(J, g.Cin, g.Cout, g.KH * g.KW)) return 0;
     // The shifted (per-tap) operand is replicated KH*KW times along the M dimension: shift the one with fewer
     // channels.  For a "same" convolution the sum over output pixels of g[co,px] x[ci,px+s] equals the sum
     // over input pixels of x[ci,px'] g[co,px'-s]: exchange the operands, mirror the taps.

@@ -539,7 +539,7 @@ int try_launch_conv_tma(int mode, cudaStream_t st, const ConvKArgs& a) {
     const int W = g.W;
     const long long s_ss = fwd ? g.in_sstride : g.out_sstride;
     const long long J = (long long)g.batch * Hd * W;
-    if (get_tc_mode() == 1 && J < 1024) return 0;
+    if (get_tc_mode() == 1 && !tc_worth_it(J, Cs, Cd, g.KH * g.KW)) return 0;
     // the tile is 128 consecutive pixels made of full rows: W in {4, 8, 16, 32}; it either divides an image or
     // holds whole images
     if (W < 4 || W > 32 || (TC_M % W) != 0 || (s_ss & 3)) return 0;

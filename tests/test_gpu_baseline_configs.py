@@ -86,7 +86,8 @@ def test_chest_comp_rho_with_config_flags(kind, tmp_path):
     assert size == 4
     assert abs(i - int(g["rho1_iters"])) <= 1
     # per-iteration lambda: ReLU-kink noise of the full-size models (1e-3 relative on Hv) enters lambda linearly
-    np.testing.assert_allclose(lam[:m], traj_ref[:m, 1], rtol=5e-3, atol=1e-6)
+    # (the verbose log prints %f: 1e-6 absolute resolution; the first lambda, at the start vector, is ~2e-4)
+    np.testing.assert_allclose(lam[:m], traj_ref[:m, 1], rtol=5e-3, atol=5e-6)
     if i == int(g["rho1_iters"]):
         assert abs(st.rho - float(g["rho1_rho"])) <= 5e-3 * float(g["rho1_rho"])
         st.g = max(0.0, st.rho - st.K, st.Kmin - st.rho)
