@@ -386,7 +386,10 @@ int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a0) {
     const int mtiles = (g.KH * g.KW * g.Cin + TC_M - 1) / TC_M;
     const int ntiles = (g.Cout + BN - 1) / BN;
     const int nkb = (int)((J + TC_KB - 1) / TC_KB);
-    int ksplit = std::max(1, kNumSMs / (mtiles * ntiles));
+    // CTAs of one launch: the weight gradient is a leaf on a side stream; the fewer SMs it holds at a time, the less the
+    // latency-bound adjoint chain on the main stream waits for an SM (B2S_WG_MAXCTAS, default: all SMs)
+    static const int max_ctas = getenv("B2S_WG_MAXCTAS") ? std::max(1, atoi(getenv("B2S_WG_MAXCTAS"))) : kNumSMs;
+    int ksplit = std::max(1, max_ctas / (mtiles * ntiles));
     static const int min_kb = getenv("B2S_WG_MINKB") ? atoi(getenv("B2S_WG_MINKB")) : 8;
     ksplit = std::min(ksplit, std::max(1, nkb / min_kb));      // at least min_kb k-blocks per CTA and pair
     switch (BN) {

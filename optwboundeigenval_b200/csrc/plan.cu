@@ -844,7 +844,12 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     p->bn_rv.assign(max_slot + 1, nullptr);
     int rc = 0;
     auto fail = [&](int code) { b2s_plan_destroy(p); return code; };
-    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the adjoint chain runs at the highest stream priority, the weight-gradient leaves at the lowest: thread blocks of a
+    // chain kernel are dispatched ahead of pending leaf blocks whenever an SM frees up (B2S_STREAM_PRIO=0: equal)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char* e = getenv("B2S_STREAM_PRIO")) { if (atoi(e) == 0) prio_lo = prio_hi = 0; }
+    if (cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -853,7 +858,7 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     }
     if (const char* e = getenv("B2S_SIDE_STREAMS")) p->n_side = std::max(1, std::min((int)b2s_plan::kMaxSide, atoi(e)));
     for (int i = 0; i < p->n_side; ++i) {
-        if (cudaStreamCreateWithFlags(&p->sides[i], cudaStreamNonBlocking) != cudaSuccess ||
+        if (cudaStreamCreateWithPriority(&p->sides[i], cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->ev_joins[i], cudaEventDisableTiming) != cudaSuccess) {
             set_error("b2s_plan_create: side stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
             return fail(-2);

@@ -14,8 +14,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R = sys.argv[1] if len(sys.argv) > 1 else "r1"
-SRC = os.path.join(ROOT, "gpurun_out")
-DST = os.path.join(ROOT, "profiles")
+SRC = os.environ.get("B2S_PROFILE_SRC", os.path.join(ROOT, "gpurun_out"))
+DST = os.environ.get("B2S_PROFILE_DST", os.path.join(ROOT, "profiles"))
 KEEP = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
@@ -99,6 +99,9 @@ def main():
     wg = summarize_rep("conv_wgrad")
     summarize_rep("bn")
     vec = summarize_rep("vec")
+    vgg = summarize_rep("vgg_conv_tc")
+    vggw = summarize_rep("vgg_wgrad")
+    summarize_rep("vgg_bn")
     def per_launch(rows):
         per = []
         for r in rows:
@@ -111,11 +114,12 @@ def main():
         return per
 
     js = {}
-    for key, rows, what in (("conv_tma_kernel (fwd + dgrad instances)", conv, "conv_tma"), ("conv_wgrad", wg, "conv_wgrad")):
+    for key, rows, what in (("conv_tma_kernel (fwd + dgrad instances)", conv, "conv_tma"), ("conv_wgrad", wg, "conv_wgrad"),
+                            ("chest_vgg conv_tc_kernel", vgg, "vgg_conv_tc"), ("chest_vgg conv_wgrad", vggw, "vgg_wgrad")):
         if rows:
             per = per_launch(rows)
             js[key] = {"capture": "%s_%s.ncu-rep: ncu --set full --clock-control none, %d consecutive launches of the Hv pass "
-                                  "(DenseNet3, batch 32, eager launches)" % (R, what, len(per)),
+                                  "(%s, eager launches)" % (R, what, len(per), "VGG16-bn, batch 4" if what.startswith("vgg") else "DenseNet3, batch 32"),
                        "dram_bytes_per_launch": sum(p["dram_bytes"] for p in per) / len(per), "launches": per}
     if js:
         with open(os.path.join(DST, "%s_ncu_top_kernel.json" % R), "w") as fh:
