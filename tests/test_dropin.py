@@ -95,3 +95,28 @@ def test_wbce_coefficients_match_the_loss():
         z = torch.randn(4, 3, generator=g)
         mine = (coef * torch.nn.functional.binary_cross_entropy_with_logits(z, t, reduction="none")).sum()
         assert abs(float(mine) - float(zoo.WeightedBCEWithLogits()(z, degenerate))) < 1e-6
+
+
+@needs_ref
+def test_remaining_reference_model_classes_trace():
+    """dcnn.MyAlexNet (six chestxray_mu0_0*_K*.py files), dcnn.DenseNet121 on dnet.py's custom autograd Functions
+    (chestxray_best.py, chestxray_mu0.py) and dcnn.MyResNet50 (cifar100_ResNet_mu0.py) lower to tapes: residual adds,
+    `_relu` / `_linear` leaf modules, 11x11 stride-4 and 7x7 stride-2 convolutions, 3x3 stride-2 max pools."""
+    import contextlib
+    import io
+    import torch
+    from optwboundeigenval_b200 import tracer
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import reference_access as ra
+    ra.import_reference(REF)
+    want = {"chest_alexnet": ((3, 224, 224), 4846414, 0), "chest_dnet121": ((3, 224, 224), 6968206, 0),
+            "chest_resnet50": ((3, 1024, 1024), 42399822, 16)}
+    for kind, (shape, n_params, n_add) in want.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            model, loss = ra.ref_model(kind)
+        tape = tracer.trace(model, loss, shape)
+        assert tape.n_params == n_params == sum(p.numel() for p in model.parameters())
+        assert sum(1 for o in tape.ops if o.kind == tracer.OP_ADD) == n_add
+        assert tape.head in (tracer.HEAD_WBCE, tracer.HEAD_SIGMOID_WBCE)
+    # dnet's classifier is Linear -> Sigmoid behind a custom Function: the sigmoid is folded into the head
+    assert tracer.trace(ra.ref_model("chest_dnet121")[0], loss, (3, 224, 224)).head == tracer.HEAD_SIGMOID_WBCE
