@@ -53,6 +53,8 @@ int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a);
 inline bool tc_worth_it(long long J, int Cs, int Cd, int KHW) {
     return J >= 1024 || (J >= 64 && (double)J * Cs * Cd * KHW >= 4.0e6);
 }
+// split-K of under-filled layers (conv_tc.cu): off for the base pass, whose summation order stays deterministic
+void set_tc_splitk_allowed(bool on);
 // 0 = never, 1 = automatic (default), 2 = whenever legal (tests)
 void set_tc_mode(int mode);
 int get_tc_mode();

@@ -103,6 +103,8 @@ long long tc_pack_floats(int Cs, int Cd, int KHW) {
     return (long long)ntiles * KHW * nchunks * 2 * BN * TC_KB;
 }
 
+bool tc_splitk_allowed();
+
 bool tc_shape_ok(int Cs, int Cd, int Hs, int Ws) {
     return Cs >= 8 && Cd >= 8 && Hs < 32768 && Ws < 32768;
 }
@@ -126,13 +128,31 @@ int launch_tc_pack(cudaStream_t st, const TcPackJob* d_jobs, int njobs, long lon
 // lanes whose tap falls outside the image read this instead (stride 0): their loads need no predicate
 __device__ const float tc_zero_words[4] = {0.f, 0.f, 0.f, 0.f};
 
+// Virtual tile -> (pixel tile, channel tile, k-slice).  Split-K (a.k_chunk = number of slices > 1) cuts the pair-tap
+// range [0, npairs * KH * KW) of a tile into slices handled by different CTAs, so that layers with few pixel tiles
+// (VGG16 conv5_x at batch 4: 28 tiles for 148 SMs, 288 k-blocks each) fill the machine; the partial tiles are added
+// with fp32 atomics (tc_store_tile_split).
+__device__ __forceinline__ void tc_decode_tile(const ConvKArgs& a, const int n_jt, const int vt, const int Cd_unused,
+                                               int& jt, int& nt, int& pt0, int& pt1) {
+    (void)Cd_unused;
+    const int PT = a.npairs * a.g.KH * a.g.KW;
+    const int ksplit = a.k_chunk > 1 ? a.k_chunk : 1;
+    const int real = vt / ksplit, ks = vt - real * ksplit;       // slices of a tile are neighbours: they share the A tile in L2
+    jt = real % n_jt;
+    nt = real / n_jt;
+    const int per = (PT + ksplit - 1) / ksplit;
+    pt0 = min(PT, ks * per);
+    pt1 = min(PT, pt0 + per);
+}
+
 template <int MODE>
 struct TcCursor {
     // geometry is re-read from the kernel parameters (constant bank) instead of being cached in
     // registers: this role keeps two 32-value load buffers live
     const ConvKArgs& a;
     int r;                 // pixel row of this thread inside the tile
-    int tile, p, ky, kx, cc;
+    int tile, p, ky, kx, cc;   // tile = VIRTUAL tile: (pixel tile, channel tile, k-slice), see tc_decode_tile
+    int pt, pt_end;            // pair-tap index (p * KHW + tap) and the end of this k-slice
     uint32_t kbg;
     int y, x;              // destination pixel (y < 0: past the end of the pixel range)
     long long nbase;       // sample offset in the source
@@ -151,11 +171,14 @@ struct TcCursor {
 
     __device__ __forceinline__ TcCursor(const ConvKArgs& a_, int r_) : a(a_), r(r_) {}
     __device__ __forceinline__ void start(int total_tiles) {
-        tile = blockIdx.x; p = 0; ky = 0; kx = 0; cc = 0; kbg = 0;
+        tile = blockIdx.x; p = 0; ky = 0; kx = 0; cc = 0; kbg = 0; pt = 0; pt_end = 0;
         if (tile < total_tiles) { set_tile(); set_tap(); }
     }
     __device__ __forceinline__ void set_tile() {
-        const int jt = tile % n_jt();
+        int jt_, nt_, pt0_, pt1_;
+        tc_decode_tile(a, n_jt(), tile, MODE == MODE_FWD ? a.g.Cout : a.g.Cin, jt_, nt_, pt0_, pt1_);
+        pt = pt0_; pt_end = pt1_;
+        const int jt = jt_;
         const long long j = (long long)jt * TC_M + r;
         const int HWd = Hd() * Wd();
         y = -1; x = 0; nbase = 0;
@@ -169,6 +192,13 @@ struct TcCursor {
     }
     __device__ __forceinline__ void set_tap() {
         const ConvGeom& g = a.g;
+        {
+            const int KHW = g.KH * g.KW;
+            p = pt / KHW;
+            const int t = pt - p * KHW;
+            ky = t / g.KW;
+            kx = t - ky * g.KW;
+        }
         int sy, sx;
         bool ok;
         if (MODE == MODE_FWD) {
@@ -189,17 +219,10 @@ struct TcCursor {
         ++kbg;
         if (++cc < nchunks()) return true;
         cc = 0;
-        if (++kx == a.g.KW) {
-            kx = 0;
-            if (++ky == a.g.KH) {
-                ky = 0;
-                if (++p == a.npairs) {
-                    p = 0;
-                    tile += gridDim.x;
-                    if (tile >= total_tiles) return false;
-                    set_tile();
-                }
-            }
+        if (++pt == pt_end) {
+            tile += gridDim.x;
+            if (tile >= total_tiles) return false;
+            set_tile();
         }
         set_tap();
         return true;
@@ -304,7 +327,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
     const int KBp = KHW * nchunks;                            // k-blocks per pair
     const int n_jt = (int)((J + TC_M - 1) / TC_M);
     const int n_nt = (Cd + BN - 1) / BN;
-    const int total_tiles = n_jt * n_nt;
+    const int ksplit = a.k_chunk > 1 ? a.k_chunk : 1;
+    const int total_tiles = n_jt * n_nt * ksplit;               // virtual tiles (tc_decode_tile)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -373,15 +397,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t kbg = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int jt = tile % n_jt, nt = tile / n_jt;
+            int jt, nt, pt0, pt1;
+            tc_decode_tile(a, n_jt, tile, Cd, jt, nt, pt0, pt1);
             float acc[BN];
 #pragma unroll
             for (int i = 0; i < BN; ++i) acc[i] = 0.f;
             constexpr int NACC = tc_nacc(BN);
             const int last_ksteps = (Cs - (nchunks - 1) * TC_KB + 7) >> 3;
-            for (int p = 0; p < a.npairs; ++p) {
-                const float sc = a.scale[p];
-                for (int kbl = 0; kbl < KBp; ++kbl) {
+            for (int pt = pt0; pt < pt1; ++pt) {
+                const float sc = a.scale[pt / KHW];
+                for (int kbl = 0; kbl < nchunks; ++kbl) {
                     const int b = kbg & 1;
                     if (tid == 256) tc_stamp(a.trace, 2, kbg, 0);
                     mbar_wait(&d_full[b], (kbg >> 1) & 1);
@@ -430,7 +455,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
                 const int m0 = nt * BN;
                 const long long off = (long long)n * d_ss + pix + (long long)m0 * HWd;
                 const int mrem = Cd - m0;                 // valid channels of this tile
-                tc_store_tile<BN>(acc, a, off, HWd, m0, mrem);
+                if (ksplit > 1) tc_store_tile_split<BN>(acc, a, off, HWd, m0, mrem, pt0 == 0);
+                else tc_store_tile<BN>(acc, a, off, HWd, m0, mrem);
             }
         }
     } else {
@@ -446,7 +472,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
             constexpr int NACC = tc_nacc(BN);
             uint32_t kbg = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                for (int pt = 0; pt < a.npairs * KHW; ++pt) {
+                int jt_, nt_, pt0, pt1;
+                tc_decode_tile(a, n_jt, tile, Cd, jt_, nt_, pt0, pt1);
+                for (int pt = pt0; pt < pt1; ++pt) {
                     for (int cc = 0; cc < nchunks; ++cc) {
                         const int ksteps = cc == nchunks - 1 ? last_ksteps : TC_KB / 8;
                         const int s = kbg % TC_NST;
@@ -492,10 +520,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
             // ===================== B producer: bulk copies of the packed weight images ===============
             uint32_t kbg = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile / n_jt;
-                for (int p = 0; p < a.npairs; ++p) {
+                int jt_, nt, pt0, pt1;
+                tc_decode_tile(a, n_jt, tile, Cd, jt_, nt, pt0, pt1);
+                for (int pt = pt0; pt < pt1; ++pt) {
+                    const int p = pt / KHW;
                     const float* __restrict__ img = a.pack[p] + (long long)nt * KBp * 2 * B_TILE_FLOATS;
-                    for (int kbl = 0; kbl < KBp; ++kbl) {
+                    for (int kbl = (pt - p * KHW) * nchunks; kbl < (pt - p * KHW + 1) * nchunks; ++kbl) {
                         const int s = kbg % TC_NST;
                         const uint32_t round = kbg / TC_NST;
                         if (lane == 0) {
@@ -521,7 +551,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvKArgs 
 }
 
 template <int BN, int MODE>
-static int launch_tc_t(cudaStream_t st, const ConvKArgs& a, long long J, int Cd) {
+static int launch_tc_t(cudaStream_t st, const ConvKArgs& a_in, long long J, int Cd) {
     constexpr size_t smem = (size_t)TC_NST * 2 * BN * TC_KB * sizeof(float) + 256;
     static bool attr_set = false;
     if (!attr_set) {
@@ -529,7 +559,34 @@ static int launch_tc_t(cudaStream_t st, const ConvKArgs& a, long long J, int Cd)
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
         attr_set = true;
     }
-    const long long tiles = ((J + TC_M - 1) / TC_M) * ((Cd + BN - 1) / BN);
+    long long tiles = ((J + TC_M - 1) / TC_M) * ((Cd + BN - 1) / BN);
+    ConvKArgs a = a_in;
+    a.k_chunk = 1;
+    {   // split-K for layers whose tiles fill less than half of the SMs (tc_decode_tile)
+        static const int enabled = getenv("B2S_TC_SPLITK") ? atoi(getenv("B2S_TC_SPLITK")) : 1;
+        const int Cs = MODE == MODE_FWD ? a.g.Cin : a.g.Cout;
+        const int nchunks = (Cs + TC_KB - 1) / TC_KB;
+        const int PT = a.npairs * a.g.KH * a.g.KW;
+        if (enabled && tc_splitk_allowed() && a.relu_mode != 1 && tiles * 2 <= kNumSMs && PT >= 2) {
+            int ksplit = (int)std::min<long long>(PT, kNumSMs / tiles);
+            while (ksplit > 1 && ((PT + ksplit - 1) / ksplit) * nchunks < 6) --ksplit;     // >= 6 k-blocks per slice
+            if (ksplit > 1) {
+                const int per = (PT + ksplit - 1) / ksplit;
+                ksplit = (PT + per - 1) / per;                                              // no empty slice
+            }
+            if (ksplit > 1) {
+                a.k_chunk = ksplit;
+                tiles *= ksplit;
+                if (!a.accumulate) {           // the partial tiles are added with atomics: start from zero
+                    const int HWd = MODE == MODE_FWD ? a.g.OH * a.g.OW : a.g.H * a.g.W;
+                    const long long d_ss = MODE == MODE_FWD ? a.g.out_sstride : a.g.in_sstride;
+                    cudaError_t e = cudaMemset2DAsync(a.out, (size_t)d_ss * sizeof(float), 0, (size_t)Cd * HWd * sizeof(float),
+                                                      (size_t)a.g.batch, st);
+                    if (e != cudaSuccess) { set_error("conv_tc split-K: cudaMemset2DAsync: %s", cudaGetErrorString(e)); return -2; }
+                }
+            }
+        }
+    }
     const unsigned grid = (unsigned)std::min<long long>(tiles, kNumSMs);
     static const bool want_trace = getenv("B2S_TC_TRACE") != nullptr;
     static int traced = 0;
@@ -573,6 +630,12 @@ static int launch_tc_mode(cudaStream_t st, const ConvKArgs& a, long long J, int 
     default: return launch_tc_t<128, MODE>(st, a, J, Cd);
     }
 }
+
+// The base pass (values, ReLU / max-pool decisions, gradient) keeps the deterministic single-CTA-per-tile summation:
+// its decisions are what every later pass is conditioned on.  The jet passes (linear given the decisions) may split.
+static thread_local bool g_splitk_allowed = true;
+void set_tc_splitk_allowed(bool on) { g_splitk_allowed = on; }
+bool tc_splitk_allowed() { return g_splitk_allowed; }
 
 int try_launch_conv_tc(int mode, cudaStream_t st, const ConvKArgs& a) {
     if (g_tc_mode == 0) return 0;

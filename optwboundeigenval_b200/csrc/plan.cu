@@ -611,7 +611,14 @@ static int backward_correction(b2s_plan* p) {
     return 0;
 }
 
+static int run_pass_eager_impl(b2s_plan* p, int K);
 static int run_pass_eager(b2s_plan* p, int K) {
+    set_tc_splitk_allowed(K != 0 && K != 4);      // base and evaluation passes: deterministic summation (conv_tc.cu)
+    const int rc = run_pass_eager_impl(p, K);
+    set_tc_splitk_allowed(true);
+    return rc;
+}
+static int run_pass_eager_impl(b2s_plan* p, int K) {
     if (K == 3) return backward_correction(p);
     if (K == 4) {                      // evaluation pass: local to the rank, no collective
         Comm* comm = p->comm;

@@ -237,4 +237,29 @@ __device__ __forceinline__ void tc_store_tile(float (&acc)[BN], const ConvKArgs&
     }
 }
 
+
+// Split-K form: this CTA holds a PARTIAL tile; partial tiles are summed with fp32 atomics into an output that was
+// zeroed beforehand (overwrite mode) or already holds the value to accumulate onto.  The ReLU mask of relu_mode 2 is
+// multiplicative, so it is applied to every partial; the bias is added by the slice that starts at pair-tap 0.
+template <int BN>
+__device__ __forceinline__ void tc_store_tile_split(float (&acc)[BN], const ConvKArgs& a, const long long off, const int cs, const int m0,
+                                                    const int mrem, const bool first_slice) {
+    float* __restrict__ outp = a.out + off;
+    const float* __restrict__ refp = a.relu_mode == 2 ? a.relu_ref + off : nullptr;
+#pragma unroll
+    for (int i0 = 0; i0 < BN; i0 += 8) {
+        float ref[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ref[i] = (refp && i0 + i < mrem) ? __ldg(refp + (long long)(i0 + i) * cs) : 1.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i0 + i < mrem) {
+                float val = acc[i0 + i];
+                if (first_slice && a.bias) val += __ldg(a.bias + m0 + i0 + i);
+                if (ref[i] > 0.f) atomicAdd(outp + (long long)(i0 + i) * cs, val);
+            }
+        }
+    }
+}
+
 }  // namespace b2s

