@@ -19,6 +19,7 @@
 // Eligible: stride 1, horizontal shift in {-1, 0, +1}, OW and W multiples of 4.
 // Everything else stays on the CUDA-core kernel (conv.cu).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "conv_args.h"
@@ -366,12 +367,19 @@ int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a0) {
     ConvKArgs a = a0;
     ConvGeom& g = a.g;
     const long long J = (long long)g.batch * g.OH * g.OW;
-    if (g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || g.KW - 1 - g.pw > 1 || g.pw > 1) return 0;
-    if (((uintptr_t)a.out & 3) != 0 || (g.in_sstride & 3) || (g.out_sstride & 3)) return 0;
+    static const bool dbg = getenv("B2S_WG_DEBUG") != nullptr;
+#define WG_REJECT(why)                                                                                                   \
+    do {                                                                                                                  \
+        if (dbg) fprintf(stderr, "wgrad_tc: Cin %d Cout %d %dx%d k%d J %lld not eligible: %s\n", g.Cin, g.Cout, g.H, g.W, g.KH, J, why); \
+        return 0;                                                                                                         \
+    } while (0)
+    if (g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || g.KW - 1 - g.pw > 1 || g.pw > 1) WG_REJECT("stride / width / padding");
+    if (((uintptr_t)a.out & 3) != 0 || (g.in_sstride & 3) || (g.out_sstride & 3)) WG_REJECT("sample stride alignment");
     for (int p = 0; p < a.npairs; ++p)
-        if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) return 0;
-    if (J >= (1LL << 31) || (long long)g.Cin * g.H * g.W >= (1LL << 31) || (long long)g.Cout * g.OH * g.OW >= (1LL << 31)) return 0;
-    if (mode == 1 && !tc_worth_it(J, g.Cin, g.Cout, g.KH * g.KW)) return 0;
+        if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) WG_REJECT("operand pointer alignment");
+    if (J >= (1LL << 31) || (long long)g.Cin * g.H * g.W >= (1LL << 31) || (long long)g.Cout * g.OH * g.OW >= (1LL << 31)) WG_REJECT("index range");
+    if (mode == 1 && !tc_worth_it(J, g.Cin, g.Cout, g.KH * g.KW)) WG_REJECT("too little work");
+#undef WG_REJECT
     // The shifted (per-tap) operand is replicated KH*KW times along the M dimension: shift the one with fewer
     // channels.  For a "same" convolution the sum over output pixels of g[co,px] x[ci,px+s] equals the sum
     // over input pixels of x[ci,px'] g[co,px'-s]: exchange the operands, mirror the taps.
