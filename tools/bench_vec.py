@@ -19,7 +19,6 @@ def measure(n, iters=50, warmup=5):
     try:
         v0 = torch.full((n,), 1.0 / n ** 0.5, dtype=torch.float64, device="cuda")
         hv = torch.randn(n, dtype=torch.float32, device="cuda")
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
         cfg = _lib.PowerCfg()
         cfg.max_iter, cfg.eps, cfg.precond = iters + warmup + 4, 0.0, 0
         _lib.check(lib.b2s_pi_reset(st, ctypes.c_void_p(v0.data_ptr()), ctypes.byref(cfg), None))
@@ -33,7 +32,6 @@ def measure(n, iters=50, warmup=5):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        del flush
     finally:
         lib.b2s_pi_destroy(st)
     bytes_ = 52.0 * n
