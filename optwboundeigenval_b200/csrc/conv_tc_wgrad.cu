@@ -16,8 +16,9 @@
 // tensor core (SS MMA).  The grid splits the pixel range (split-K) so that all 148 SMs work; each CTA
 // atomically adds its partial tile into the flat gradient vector.
 //
-// Eligible: stride 1, horizontal shift in {-1, 0, +1}, OW and W multiples of 4.
-// Everything else stays on the CUDA-core kernel (conv.cu).
+// 128-bit variant: stride 1, horizontal shift in {-1, 0, +1}, OW and W multiples of 4.  Every other geometry takes the
+// scalar-gather variant (VEC = false: one predicated load per element, pixels decoded one by one).
+// Contractions too small to be worth a tensor-core launch stay on the CUDA-core kernel (conv.cu).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -50,7 +51,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
 }
 
-template <int BN>
+template <int BN, bool VEC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, const int ksplit, const int swapped) {
     extern __shared__ __align__(1024) uint8_t wg_smem[];
@@ -127,7 +128,7 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
             const int ky = t / g.KW, kx = t - ky * g.KW;
             dyv[q] = ky - g.ph;
             dxv[q] = kx - g.pw;
-            rowoff[q] = ci * HW + dyv[q] * g.W;
+            rowoff[q] = ci * HW + dyv[q] * g.W + (VEC ? 0 : dxv[q]);
         }
         constexpr int NB = BN / 16;                          // B patches of this warp
         int boff[NB];
@@ -148,6 +149,12 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
             float* Alo = Ahi + WG_A_FLOATS;
             float* Bhi = Alo + WG_A_FLOATS;
             float* Blo = Bhi + S::B_FLOATS;
+            const float* __restrict__ xp = a.act[p];
+            const float* __restrict__ gp = a.wt[p];
+            float4 ca[4][2];
+            float ea[4][2];
+            float4 cb[NB];
+            if (VEC) {
             // the two 4-pixel groups of this lane inside the k-block: k-groups l4 and l4 + 4
             int oy_[2], ox_[2];
             long long xo[2], go[2];
@@ -164,11 +171,7 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
                 xo[h] = (long long)n * g.in_sstride + oy_[h] * g.W + ox_[h];
                 go[h] = (long long)n * g.out_sstride + rem;
             }
-            const float* __restrict__ xp = a.act[p];
-            const float* __restrict__ gp = a.wt[p];
             // ---- issue every load of this warp's share of the stage
-            float4 ca[4][2];
-            float ea[4][2];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!gok[q]) continue;
@@ -184,12 +187,53 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
                     ea[q][h] = e;
                 }
             }
-            float4 cb[NB];
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
                 const int h = (wq + 4 * u) & 1;
                 const bool ok = pv[h] && bok[u];
                 cb[u] = ok ? __ldg(reinterpret_cast<const float4*>(gp + go[h] + boff[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            } else {
+                // general geometry (any width, stride, kernel size): the four pixels of a k-group are decoded one by one
+                // (a group may straddle image rows or samples) and every element is one predicated scalar load; the tap
+                // shift is part of rowoff.  Serves the 14 x 14 / 7 x 7 maps of the chest models (VGG16 conv5_x, DenseNet121
+                // blocks 3 / 4), whose rows are not 16-byte aligned.
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long j = (long long)kb * TC_KB + (h * 4 + l4) * 4;
+                    const unsigned jj = j < J ? (unsigned)j : 0u;
+                    int n = (int)(jj / (unsigned)OHW);
+                    const int rem = (int)(jj - (unsigned)n * OHW);
+                    int oy = rem / g.OW;
+                    int ox = rem - oy * g.OW;
+                    float av[4][4], bv[NB][4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool pv = j + e < J;
+                        const int iy0 = oy * g.sh, ix0 = ox * g.sw;
+                        const float* __restrict__ xb = xp + (long long)n * g.in_sstride + iy0 * g.W + ix0;
+                        const float* __restrict__ gb = gp + (long long)n * g.out_sstride + oy * g.OW + ox;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bool ok = gok[q] && rok[q] && pv && (unsigned)(iy0 + dyv[q]) < (unsigned)g.H &&
+                                            (unsigned)(ix0 + dxv[q]) < (unsigned)g.W;
+                            av[q][e] = ok ? __ldg(xb + rowoff[q]) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < NB; ++u) {
+                            if (((wq + 4 * u) & 1) == h) bv[u][e] = (pv && bok[u]) ? __ldg(gb + boff[u]) : 0.f;
+                        }
+                        if (++ox == g.OW) { ox = 0; if (++oy == g.OH) { oy = 0; ++n; } }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ca[q][h] = make_float4(av[q][0], av[q][1], av[q][2], av[q][3]);
+                        ea[q][h] = 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < NB; ++u)
+                        if (((wq + 4 * u) & 1) == h) cb[u] = make_float4(bv[u][0], bv[u][1], bv[u][2], bv[u][3]);
+                }
             }
             // ---- the stage must have been read by the MMAs of its previous use
             if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
@@ -201,8 +245,10 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float4 v = ca[q][h];
-                    if (dxv[q] < 0) v = make_float4(ea[q][h], v.x, v.y, v.z);
-                    else if (dxv[q] > 0) v = make_float4(v.y, v.z, v.w, ea[q][h]);
+                    if (VEC) {
+                        if (dxv[q] < 0) v = make_float4(ea[q][h], v.x, v.y, v.z);
+                        else if (dxv[q] > 0) v = make_float4(v.y, v.z, v.w, ea[q][h]);
+                    }
                     float4 hi, lo;
                     split4(v, hi, lo);
                     const int o = rg * 256 + h * 128 + lane * 4;       // ((rg*8 + kgroup) * 32) + (row%8)*4, kgroup = h*4 + lane/8
@@ -347,17 +393,21 @@ conv_tc_wgrad_kernel(const ConvKArgs a, const int mtiles, const int ntiles, cons
     }
 }
 
-template <int BN>
-static int launch_wg_t(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntiles, int ksplit, int swapped) {
+template <int BN, bool VEC>
+static int launch_wg_v(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntiles, int ksplit, int swapped) {
     constexpr size_t smem = WgSmem<BN>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
         attr_set = true;
     }
-    conv_tc_wgrad_kernel<BN><<<mtiles * ntiles * ksplit, TC_THREADS, smem, st>>>(a, mtiles, ntiles, ksplit, swapped);
+    conv_tc_wgrad_kernel<BN, VEC><<<mtiles * ntiles * ksplit, TC_THREADS, smem, st>>>(a, mtiles, ntiles, ksplit, swapped);
     return 1;
+}
+template <int BN>
+static int launch_wg_t(cudaStream_t st, const ConvKArgs& a, int mtiles, int ntiles, int ksplit, int swapped, bool vec) {
+    return vec ? launch_wg_v<BN, true>(st, a, mtiles, ntiles, ksplit, swapped) : launch_wg_v<BN, false>(st, a, mtiles, ntiles, ksplit, swapped);
 }
 
 // Returns 1 when the tensor-core kernel was launched, 0 when the layer is not eligible, <0 on error.
@@ -373,10 +423,15 @@ int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a0) {
         if (dbg) fprintf(stderr, "wgrad_tc: Cin %d Cout %d %dx%d k%d J %lld not eligible: %s\n", g.Cin, g.Cout, g.H, g.W, g.KH, J, why); \
         return 0;                                                                                                         \
     } while (0)
-    if (g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || g.KW - 1 - g.pw > 1 || g.pw > 1) WG_REJECT("stride / width / padding");
-    if (((uintptr_t)a.out & 3) != 0 || (g.in_sstride & 3) || (g.out_sstride & 3)) WG_REJECT("sample stride alignment");
+    // 128-bit loads need stride 1, rows that start 16-byte aligned and a horizontal shift of at most one pixel; every
+    // other geometry (14 x 14 and 7 x 7 maps, strided or wide kernels) takes the scalar-gather variant of the transform
+    static const int scalar_ok = getenv("B2S_WG_SCALAR") ? atoi(getenv("B2S_WG_SCALAR")) : 1;
+    bool vec = !(g.sh != 1 || g.sw != 1 || (g.OW & 3) || (g.W & 3) || g.KW - 1 - g.pw > 1 || g.pw > 1) &&
+               !((g.in_sstride & 3) || (g.out_sstride & 3));
     for (int p = 0; p < a.npairs; ++p)
-        if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) WG_REJECT("operand pointer alignment");
+        if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) vec = false;
+    if (!vec && !scalar_ok) WG_REJECT("stride / width / padding / alignment (scalar variant disabled)");
+    if ((uintptr_t)a.out & 3) WG_REJECT("output alignment");
     if (J >= (1LL << 31) || (long long)g.Cin * g.H * g.W >= (1LL << 31) || (long long)g.Cout * g.OH * g.OW >= (1LL << 31)) WG_REJECT("index range");
     if (mode == 1 && !tc_worth_it(J, g.Cin, g.Cout, g.KH * g.KW)) WG_REJECT("too little work");
 #undef WG_REJECT
@@ -401,12 +456,12 @@ int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a0) {
     static const int min_kb = getenv("B2S_WG_MINKB") ? atoi(getenv("B2S_WG_MINKB")) : 8;
     ksplit = std::min(ksplit, std::max(1, nkb / min_kb));      // at least min_kb k-blocks per CTA and pair
     switch (BN) {
-    case 16: return launch_wg_t<16>(st, a, mtiles, ntiles, ksplit, swapped);
-    case 32: return launch_wg_t<32>(st, a, mtiles, ntiles, ksplit, swapped);
-    case 48: return launch_wg_t<48>(st, a, mtiles, ntiles, ksplit, swapped);
-    case 64: return launch_wg_t<64>(st, a, mtiles, ntiles, ksplit, swapped);
-    case 96: return launch_wg_t<96>(st, a, mtiles, ntiles, ksplit, swapped);
-    default: return launch_wg_t<128>(st, a, mtiles, ntiles, ksplit, swapped);
+    case 16: return launch_wg_t<16>(st, a, mtiles, ntiles, ksplit, swapped, vec);
+    case 32: return launch_wg_t<32>(st, a, mtiles, ntiles, ksplit, swapped, vec);
+    case 48: return launch_wg_t<48>(st, a, mtiles, ntiles, ksplit, swapped, vec);
+    case 64: return launch_wg_t<64>(st, a, mtiles, ntiles, ksplit, swapped, vec);
+    case 96: return launch_wg_t<96>(st, a, mtiles, ntiles, ksplit, swapped, vec);
+    default: return launch_wg_t<128>(st, a, mtiles, ntiles, ksplit, swapped, vec);
     }
 }
 

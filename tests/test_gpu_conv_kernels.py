@@ -33,3 +33,20 @@ def test_tensor_core_contractions_match_fp64(W, cin, cout, batch, k):
     # the tensor-core path must not be (much) less accurate than the fp32 CUDA-core path
     for what in ("fwd", "dgrad", "wgrad"):
         assert errs[(2, what)] < 4 * errs[(0, what)] + 5e-7, (what, errs)
+
+
+@pytest.mark.parametrize("W,cin,cout,batch,k,stride,pad", [
+    (14, 64, 96, 4, 3, 1, 1),     # VGG16 conv5_x / DenseNet121 block 3 geometry: rows of 14 floats are not 16-byte aligned
+    (7, 128, 32, 8, 3, 1, 1),     # DenseNet121 block 4; 49-pixel images: k-groups straddle rows and samples
+    (14, 40, 24, 5, 5, 1, 2),     # 5 x 5 kernel: horizontal shifts of two pixels
+    (15, 24, 40, 6, 3, 2, 1),     # stride 2, odd width
+    (12, 32, 16, 7, 3, 1, 0),     # no padding: 12 -> 10 wide output
+])
+def test_weight_gradient_scalar_gather_variant_matches_fp64(W, cin, cout, batch, k, stride, pad):
+    """conv_tc_wgrad_kernel<BN, VEC=false>: geometries the 128-bit transform cannot take (widths that are not a multiple
+    of 4, strides, wide kernels).  Mode 2 forces the tensor-core kernels wherever they are legal."""
+    import tma_probe
+    errs = tma_probe.probe(W, cin, cout, batch, k, verbose=False, stride=stride, pad=pad)
+    for (mode, what), e in errs.items():
+        assert e < 1e-5, "mode %d %s: relative L2 error %.3e" % (mode, what, e)
+    assert errs[(2, "wgrad")] < 4 * errs[(0, "wgrad")] + 5e-7, errs

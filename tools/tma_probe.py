@@ -18,10 +18,10 @@ from optwboundeigenval_b200.hvp_operator import B200HVPOperator, clear_plans   #
 
 
 class TwoConv(nn.Module):
-    def __init__(self, cin, cout, k):
+    def __init__(self, cin, cout, k, stride=1, pad=None):
         super().__init__()
         self.c1 = nn.Conv2d(16, cin, 1, bias=False)
-        self.c2 = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False)
+        self.c2 = nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2 if pad is None else pad, bias=False)
         self.pool = nn.AdaptiveAvgPool2d(1)
         self.fc = nn.Linear(cout, 10)
 
@@ -36,15 +36,15 @@ def read_tensor(plan, adjoint, order, t, batch):
     return out
 
 
-def probe(W=32, cin=48, cout=12, batch=4, k=3, verbose=True):
+def probe(W=32, cin=48, cout=12, batch=4, k=3, verbose=True, stride=1, pad=None):
     """returns {(mode, what): relative L2 error against fp64} for what in fwd / dgrad / wgrad, mode in 0 (CUDA cores) / 2 (tensor cores)"""
     lib = _lib.load()
     errs = {}
     torch.manual_seed(3)
-    m = TwoConv(cin, cout, k).train()
+    m = TwoConv(cin, cout, k, stride, pad).train()
     x = torch.randn(batch, 16, W, W)
     y = torch.randint(0, 10, (batch,))
-    md = TwoConv(cin, cout, k).double()
+    md = TwoConv(cin, cout, k, stride, pad).double()
     md.load_state_dict({k_: v.double() for k_, v in m.state_dict().items()})
     h1 = md.c1(x.double())
     h1.retain_grad()
