@@ -41,15 +41,17 @@ __device__ __forceinline__ BnChan<K> from_raw(const BnChanRaw& r) {
     return ch;
 }
 
+// ovr: the order-K sums of this channel when they have just been exchanged inside the calling kernel (fsum[K] is
+// being rewritten by block (c, 0) at that moment), else NULL
 template <int K>
-__device__ inline BnChan<K> bn_channel(const BnArgs& a, int c) {
+__device__ inline BnChan<K> bn_channel(const BnArgs& a, int c, const double* ovr = nullptr) {
     BnChan<K> ch;
     const double N = (double)a.count;
     double mu[3] = {0, 0, 0}, s[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k <= K; ++k) {
-        mu[k] = a.fsum[k][0 * a.C + c] / N;
-        s[k] = a.fsum[k][1 * a.C + c] / N;
+        mu[k] = ((k == K && ovr) ? ovr[0] : a.fsum[k][0 * a.C + c]) / N;
+        s[k] = ((k == K && ovr) ? ovr[1] : a.fsum[k][1 * a.C + c]) / N;
     }
     s[0] = s[0] - mu[0] * mu[0];
     if (s[0] < 0) s[0] = 0;
@@ -185,15 +187,15 @@ __device__ __forceinline__ void bn_fwd_stats_body(const BnArgs& a) {
 
 // ---- forward apply -------------------------------------------------------------------------
 template <int K, int VEC>
-__device__ __forceinline__ void bn_fwd_apply_body(const BnArgs& a) {
+__device__ __forceinline__ void bn_fwd_apply_body(const BnArgs& a, const double* ovr = nullptr) {
     __shared__ BnChanRaw sch;
     const int c = blockIdx.x;
     if (threadIdx.x == 0) {
-        to_raw<K>(bn_channel<K>(a, c), sch);
+        to_raw<K>(bn_channel<K>(a, c, ovr), sch);
         if (K == 0 && blockIdx.y == 0 && a.running_mean) {
             const double N = (double)a.count;
-            const double mu = a.fsum[0][0 * a.C + c] / N;
-            double var = a.fsum[0][1 * a.C + c] / N - mu * mu;
+            const double mu = (ovr ? ovr[0] : a.fsum[0][0 * a.C + c]) / N;
+            double var = (ovr ? ovr[1] : a.fsum[0][1 * a.C + c]) / N - mu * mu;
             if (var < 0) var = 0;
             const double unb = N > 1 ? var * N / (N - 1) : var;
             const double m = (double)a.momentum;
@@ -260,7 +262,7 @@ __device__ __forceinline__ void bn_bwd_stats_body(const BnArgs& a) {
 
 // ---- backward apply: xbar_K and the parameter-gradient slices ----------------------------------
 template <int K, int VEC>
-__device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_scale) {
+__device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_scale, const double* ovr = nullptr) {
     __shared__ BnChanRaw sch;
     __shared__ float sm[2][3];
     const int c = blockIdx.x;
@@ -271,15 +273,15 @@ __device__ __forceinline__ void bn_bwd_apply_body(const BnArgs& a, float pgrad_s
         Jet<K, float> Gj, Xj;
 #pragma unroll
         for (int k = 0; k <= K; ++k) {
-            Gj.c[k] = (float)(a.bsum[k][0 * a.C + c] / N);
-            Xj.c[k] = (float)(a.bsum[k][1 * a.C + c] / N);
+            Gj.c[k] = (float)(((k == K && ovr) ? ovr[0] : a.bsum[k][0 * a.C + c]) / N);
+            Xj.c[k] = (float)(((k == K && ovr) ? ovr[1] : a.bsum[k][1 * a.C + c]) / N);
         }
         const Jet<K, float> t1 = ch0.gam * Gj, t2 = ch0.gam * Xj;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sm[0][k] = t1.c[k]; sm[1][k] = t2.c[k]; }
         if (blockIdx.y == 0) {
-            atomicAdd(a.out_beta + c, (float)(a.bsum[K][0 * a.C + c] * (double)pgrad_scale));
-            atomicAdd(a.out_gamma + c, (float)(a.bsum[K][1 * a.C + c] * (double)pgrad_scale));
+            atomicAdd(a.out_beta + c, (float)((ovr ? ovr[0] : a.bsum[K][0 * a.C + c]) * (double)pgrad_scale));
+            atomicAdd(a.out_gamma + c, (float)((ovr ? ovr[1] : a.bsum[K][1 * a.C + c]) * (double)pgrad_scale));
         }
     }
     __syncthreads();
@@ -327,6 +329,14 @@ template <int K, int VEC>
 __global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnArgs a, int do_stats) {
     pdl_trigger();
     if (do_stats) bn_fwd_stats_body<K, VEC>(a);
+    if (a.peer && a.peer_ll) {
+        // data parallel: the channel's blocks exchange its sums with the peers; the local packet is the barrier
+        // between them (no grid.sync: channels proceed independently)
+        double tot[2];
+        if (do_stats) peer_exchange_channel<2>(a.fsum[K], a.C, blockIdx.x, *a.peer, tot);
+        bn_fwd_apply_body<K, VEC>(a, do_stats ? tot : nullptr);
+        return;
+    }
     __threadfence();
     cg::this_grid().sync();
     if (a.peer && do_stats) {          // data parallel: sum the per-channel sums over the GPUs, inside this kernel
@@ -340,6 +350,12 @@ template <int K, int VEC>
 __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnArgs a, float ps) {
     pdl_trigger();
     bn_bwd_stats_body<K, VEC>(a);
+    if (a.peer && a.peer_ll) {
+        double tot[2];
+        peer_exchange_channel<2>(a.bsum[K], a.C, blockIdx.x, *a.peer, tot);
+        bn_bwd_apply_body<K, VEC>(a, ps, tot);
+        return;
+    }
     __threadfence();
     cg::this_grid().sync();
     if (a.peer) {
@@ -358,6 +374,12 @@ __global__ void __launch_bounds__(1024) bn_fwd_chan_kernel(const BnArgs a, int d
     pdl_trigger();
     pdl_wait();
     if (do_stats) bn_fwd_stats_body<K, VEC>(a);
+    if (a.peer && do_stats) {          // data parallel (peer_ll): one block per channel, so the exchange is per block
+        double tot[2];
+        peer_exchange_channel<2>(a.fsum[K], a.C, blockIdx.x, *a.peer, tot);
+        bn_fwd_apply_body<K, VEC>(a, tot);
+        return;
+    }
     __threadfence();
     __syncthreads();
     bn_fwd_apply_body<K, VEC>(a);
@@ -367,6 +389,12 @@ __global__ void __launch_bounds__(1024) bn_bwd_chan_kernel(const BnArgs a, float
     pdl_trigger();
     pdl_wait();
     bn_bwd_stats_body<K, VEC>(a);
+    if (a.peer) {
+        double tot[2];
+        peer_exchange_channel<2>(a.bsum[K], a.C, blockIdx.x, *a.peer, tot);
+        bn_bwd_apply_body<K, VEC>(a, ps, tot);
+        return;
+    }
     __threadfence();
     __syncthreads();
     bn_bwd_apply_body<K, VEC>(a, ps);
@@ -376,7 +404,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_chan_kernel(const BnArgs a, float
 static inline int bn_chan_block(const BnArgs& a, int vec) {
     const long long per_chan = (long long)a.batch * a.HW / vec;      // chunks per channel
     static const long long limit = getenv("B2S_BN_CHAN_MAX") ? atoll(getenv("B2S_BN_CHAN_MAX")) : 1024;
-    if (a.C < 16 || per_chan > limit || a.peer) return 0;       // the in-kernel exchange lives in the cooperative form
+    if (a.C < 16 || per_chan > limit || (a.peer && !a.peer_ll)) return 0;   // the block-0 exchange lives in the cooperative form
     return per_chan >= 4096 ? 1024 : per_chan >= 1024 ? 512 : 256;
 }
 

@@ -60,6 +60,7 @@ struct Comm {
     void* peer_base[kPeerMax] = {};
     unsigned long long* d_seq = nullptr;
     unsigned int* d_ticket = nullptr;
+    unsigned int* d_chan_ticket = nullptr;   // [kPeerCap + 1]: per-channel tickets, then the done ticket (peer_exchange_channel)
     int* h_error = nullptr;            // mapped pinned host memory (peer.cuh: a peer did not arrive in time)
     bool peers_ready = false;
     PeerCtx ctx = {};
@@ -108,6 +109,7 @@ int comm_destroy(Comm* c) {
     if (c->xbuf) cudaFree(c->xbuf);
     if (c->d_seq) cudaFree(c->d_seq);
     if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_chan_ticket) cudaFree(c->d_chan_ticket);
     if (c->h_error) cudaFreeHost(c->h_error);
     if (c->d_ctx) cudaFree(c->d_ctx);
     NcclApi* a = nccl();
@@ -138,6 +140,8 @@ int comm_peer_local(Comm* c, void* h_handle64) {
         B2S_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
         B2S_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
         B2S_CUDA(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+        B2S_CUDA(cudaMalloc(&c->d_chan_ticket, (kPeerCap + 1) * sizeof(unsigned int)));
+        B2S_CUDA(cudaMemset(c->d_chan_ticket, 0, (kPeerCap + 1) * sizeof(unsigned int)));
         B2S_CUDA(cudaHostAlloc(&c->h_error, sizeof(int), cudaHostAllocMapped));
         *c->h_error = 0;
         B2S_CUDA(cudaDeviceSynchronize());
@@ -169,7 +173,11 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
     for (int r = 0; r < c->world; ++r) {
         x.flag[r] = reinterpret_cast<unsigned long long*>(c->peer_base[r]);
         x.data[r] = reinterpret_cast<double*>(static_cast<char*>(c->peer_base[r]) + kPeerFlagBytes);
+        x.ll[r] = reinterpret_cast<uint4*>(static_cast<char*>(c->peer_base[r]) + kPeerLLOffset);
     }
+    x.own_ll = reinterpret_cast<uint4*>(static_cast<char*>(c->xbuf) + kPeerLLOffset);
+    x.chan_ticket = c->d_chan_ticket;
+    x.done_ticket = c->d_chan_ticket + kPeerCap;
     x.own_flag = reinterpret_cast<unsigned long long*>(c->xbuf);
     x.own_data = reinterpret_cast<double*>(static_cast<char*>(c->xbuf) + kPeerFlagBytes);
     x.seq = c->d_seq;
@@ -199,12 +207,17 @@ int comm_peer_error(Comm* c) {
 }
 void comm_peer_disable(Comm* c) { if (c) c->peers_ready = false; }
 
+// Default: the per-channel packet exchange inside the fused BatchNorm kernels (peer_exchange_channel: no grid barrier,
+// one NVLink traversal per layer; B2S_PEER_LL=0 switches it off).  The older in-kernel form -- block 0 exchanges
+// between two grid barriers, B2S_PEER_FUSED=1 -- idles the whole grid while one block talks to the peers (measured at
+// 2 GPUs, DenseNet3: 3.60 ms per step against 3.33 ms for the separate one-CTA exchange kernel and 3.35 ms for NCCL).
+int comm_peer_ll(const Comm* c) {
+    static const bool on = !(getenv("B2S_PEER_LL") && atoi(getenv("B2S_PEER_LL")) == 0);
+    return (c && c->peers_ready && on) ? 1 : 0;
+}
 const PeerCtx* comm_peer_ctx(Comm* c) {
-    // measured at 2 GPUs (DenseNet3): exchange inside the cooperative BatchNorm kernel 3.60 ms per step, separate
-    // one-CTA exchange kernel between the statistics and apply kernels 3.33 ms, NCCL 3.35 ms -- the in-kernel form
-    // idles the whole grid across two grid barriers while one block talks to the peers.  Opt-in: B2S_PEER_FUSED=1.
-    static const bool on = getenv("B2S_PEER_FUSED") && atoi(getenv("B2S_PEER_FUSED")) != 0;
-    return (c && c->peers_ready && on) ? c->d_ctx : nullptr;
+    static const bool fused = getenv("B2S_PEER_FUSED") && atoi(getenv("B2S_PEER_FUSED")) != 0;
+    return (c && c->peers_ready && (fused || comm_peer_ll(c))) ? c->d_ctx : nullptr;
 }
 
 const PeerCtx* comm_peer_tail_ctx(Comm* c) {

@@ -30,6 +30,8 @@ int comm_peer_error(Comm* c);
 struct PeerCtx;
 // device-resident exchange context for kernels that do the exchange themselves (peer.cuh), NULL when unavailable
 const PeerCtx* comm_peer_ctx(Comm* c);
+// 1 when the in-kernel exchange is the per-channel packet form (peer.cuh: peer_exchange_channel), the default
+int comm_peer_ll(const Comm* c);
 // ... for reduction kernels whose last block performs the exchange (peer_exchange_tail), NULL when unavailable
 const PeerCtx* comm_peer_tail_ctx(Comm* c);
 }  // namespace b2s

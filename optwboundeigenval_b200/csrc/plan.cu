@@ -279,6 +279,7 @@ static BnArgs bn_args(b2s_plan* p, int oi, int K) {
     a.pgrad_scale = 1.0f / (float)p->world;
     a.peer = (p->comm && 2 * a.C <= 4096) ? comm_peer_ctx(p->comm) : nullptr;
     a.peer_tail = (p->comm && 2 * a.C <= 4096) ? comm_peer_tail_ctx(p->comm) : nullptr;
+    a.peer_ll = (a.peer && comm_peer_ll(p->comm)) ? 1 : 0;
     return a;
 }
 
