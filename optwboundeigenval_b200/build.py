@@ -21,7 +21,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libb200spectral.so")
 SOURCES = ["plan.cu", "conv.cu", "bn.cu", "elementwise.cu", "head.cu", "vec.cu", "comm.cu", "kfac.cu",
-           "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tma.cu"]
+           "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tma.cu", "conv_wgrad_tma.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 if os.environ.get("B2S_BUILD_TRUNC"):          # experiment: truncating TF32 split in conv_tma.cu

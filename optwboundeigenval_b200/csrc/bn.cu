@@ -469,7 +469,9 @@ int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stat
     if (skip_family("bn_fwd")) return 0;
     const int vec = bn_vec(a);
     if (const int blk = bn_chan_block(a, vec)) {
-#define CALL(K_, V_) launch_pdl(bn_fwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, a, do_stats)
+        BnArgs b = a;
+        if (b.peer_ll == 2) { b.peer = nullptr; b.peer_ll = 0; }     // single GPU: one block per channel needs no barrier at all
+#define CALL(K_, V_) launch_pdl(bn_fwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, b, do_stats)
         B2S_BN_DISPATCH(order, vec, CALL);
 #undef CALL
         B2S_LAUNCH_CHECK();
@@ -487,7 +489,9 @@ int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     const int vec = bn_vec(a);
     if (const int blk = bn_chan_block(a, vec)) {
         const float ps = a.pgrad_scale;
-#define CALL(K_, V_) launch_pdl(bn_bwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, a, ps)
+        BnArgs b = a;
+        if (b.peer_ll == 2) { b.peer = nullptr; b.peer_ll = 0; }
+#define CALL(K_, V_) launch_pdl(bn_bwd_chan_kernel<K_, V_>, dim3(a.C, 1), dim3(blk), 0, st, b, ps)
         B2S_BN_DISPATCH(order, vec, CALL);
 #undef CALL
         B2S_LAUNCH_CHECK();

@@ -198,6 +198,50 @@ int comm_peer_attach(Comm* c, const void* h_handles) {
     return 0;
 }
 
+// ---- single-GPU form of the per-channel exchange ----------------------------------------------------------
+// world = 1: the "exchange" is the channel's last block writing two packets into local memory and the channel's other
+// blocks polling them -- a per-channel barrier in place of the grid-wide one of the cooperative BatchNorm kernels.
+struct LocalPeer {
+    void* ll = nullptr;
+    unsigned long long* seq = nullptr;
+    unsigned int* tickets = nullptr;
+    int* h_error = nullptr;
+    PeerCtx* d_ctx = nullptr;
+};
+int local_peer_create(LocalPeer** out) {
+    LocalPeer* l = new LocalPeer();
+    *out = l;
+    B2S_CUDA(cudaMalloc(&l->ll, kPeerLLBytes));
+    B2S_CUDA(cudaMemset(l->ll, 0, kPeerLLBytes));
+    B2S_CUDA(cudaMalloc(&l->seq, sizeof(unsigned long long)));
+    B2S_CUDA(cudaMemset(l->seq, 0, sizeof(unsigned long long)));
+    B2S_CUDA(cudaMalloc(&l->tickets, (kPeerCap + 1) * sizeof(unsigned int)));
+    B2S_CUDA(cudaMemset(l->tickets, 0, (kPeerCap + 1) * sizeof(unsigned int)));
+    B2S_CUDA(cudaHostAlloc(&l->h_error, sizeof(int), cudaHostAllocMapped));
+    *l->h_error = 0;
+    PeerCtx x = {};
+    x.ll[0] = x.own_ll = static_cast<uint4*>(l->ll);
+    x.seq = l->seq;
+    x.chan_ticket = l->tickets;
+    x.done_ticket = l->tickets + kPeerCap;
+    int* dev_err = nullptr;
+    B2S_CUDA(cudaHostGetDevicePointer(&dev_err, l->h_error, 0));
+    x.error = dev_err;
+    x.timeout_ns = 600ull * 1000000000ull;
+    x.rank = 0; x.world = 1;
+    B2S_CUDA(cudaMalloc(&l->d_ctx, sizeof(PeerCtx)));
+    B2S_CUDA(cudaMemcpy(l->d_ctx, &x, sizeof(PeerCtx), cudaMemcpyHostToDevice));
+    B2S_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+void local_peer_destroy(LocalPeer* l) {
+    if (!l) return;
+    cudaFree(l->ll); cudaFree(l->seq); cudaFree(l->tickets); cudaFree(l->d_ctx);
+    if (l->h_error) cudaFreeHost(l->h_error);
+    delete l;
+}
+const PeerCtx* local_peer_ctx(const LocalPeer* l) { return l ? l->d_ctx : nullptr; }
+
 int comm_peer_ready(const Comm* c) { return (c && c->peers_ready) ? 1 : 0; }
 int comm_peer_error(Comm* c) {
     if (!c || !c->h_error) return 0;

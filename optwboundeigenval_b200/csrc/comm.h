@@ -34,4 +34,9 @@ const PeerCtx* comm_peer_ctx(Comm* c);
 int comm_peer_ll(const Comm* c);
 // ... for reduction kernels whose last block performs the exchange (peer_exchange_tail), NULL when unavailable
 const PeerCtx* comm_peer_tail_ctx(Comm* c);
+// single-GPU form of the per-channel exchange: a per-channel barrier inside the cooperative BatchNorm kernels
+struct LocalPeer;
+int local_peer_create(LocalPeer** out);
+void local_peer_destroy(LocalPeer* l);
+const PeerCtx* local_peer_ctx(const LocalPeer* l);
 }  // namespace b2s

@@ -611,7 +611,8 @@ int launch_conv_wgrad(cudaStream_t st, const ConvGeom& g, int npairs, const floa
                    4.0 * npairs * ((double)g.batch * g.Cin * g.H * g.W + (double)g.batch * g.Cout * g.OH * g.OW), st);
     if (skip_family("conv_wgrad")) return 0;
     {
-        const int rc = try_launch_wgrad_tc(st, a);           // tcgen05 path
+        int rc = try_launch_wgrad_tma(st, a);                // tcgen05 path, TMA-staged (small maps: DenseNet3, USPS)
+        if (rc == 0) rc = try_launch_wgrad_tc(st, a);        // tcgen05 path, operands gathered by the transform threads
         if (rc < 0) return rc;
         if (rc == 1) {
             B2S_LAUNCH_CHECK();

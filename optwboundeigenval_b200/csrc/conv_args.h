@@ -46,6 +46,8 @@ int try_launch_conv_tma(int mode, cudaStream_t st, const ConvKArgs& a);
 // weight-gradient contraction on the tensor cores (conv_tc_wgrad.cu): a.act = x jets, a.wt = adjoint jets,
 // a.out = the layer's slice of the flat gradient.  Same return convention.
 int try_launch_wgrad_tc(cudaStream_t st, const ConvKArgs& a);
+// ... TMA-staged variant for small maps (conv_wgrad_tma.cu): W in {8, 16, 32}, stride 1, "same" size
+int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a);
 // Automatic mode: is the contraction worth a tensor-core launch?  Many pixel tiles, or few pixels but a deep
 // contraction (VGG16 conv5_x: 4 x 14 x 14 = 784 pixels with 512 x 512 x 9 MACs each; DenseNet121 blocks 3 / 4 at 14 x 14
 // and 7 x 7) -- round 1 asked for 1024 pixels only and left those layers, two thirds of the chest models' HVP time, on

@@ -34,6 +34,7 @@
 
 #include "conv_args.h"
 #include "tc_common.cuh"
+#include "tma_common.h"
 
 namespace b2s {
 
@@ -54,14 +55,6 @@ struct TmaTiling {
     int KC;                  // channels per box (8..32, multiple of 8)
     int dbg;                 // B2S_TMA_DBG: 4 = soft barrier time-outs (flag instead of trap) + synchronous launch report
 };
-
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
 
 // debug (B2S_TMA_DBG & 4): the first barrier wait that times out records its id here and every later wait
 // returns at once, so that a protocol error ends the kernel with a diagnosis instead of a trap
@@ -438,10 +431,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TmEncodeFn tm_encoder() {
+TmEncodeFn tm_encoder() {
     static TmEncodeFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;

@@ -1,0 +1,536 @@
+// conv_wgrad_tma.cu -- TMA-staged tcgen05 weight-gradient contraction for the small-map layers (sm_100a):
+// every convolution of DenseNet3 (32x32 / 16x16 / 8x8 maps) and of the USPS CNN.
+//
+//   Wbar[co][ci][ky][kx] += sum_p scale_p * sum_{n,oy,ox} g_p[n,co,oy,ox] * x_p[n,ci,oy+ky-ph,ox+kx-pw]
+//
+// Same GEMM view, 3xTF32 scheme, drain and epilogue as conv_tc_wgrad.cu (K = output pixel, A rows = (tap, channel) of
+// the shifted tensor, B rows = channels of the other one).  What changes is how the operands reach the tensor core.
+// In conv_tc_wgrad.cu every transform thread loads its share of the [128 + BN rows] x [32 pixels] stage from global
+// memory -- the shifted operand once PER TAP -- and can only ask for the next k-block once it has stored the current
+// one: a k-block costs the L2 latency plus the 9-fold re-read (measured ~1 us per k-block and CTA, 25-47 us per
+// DenseNet3 launch whatever its size).  Here:
+//
+//   * a k-block is 32 consecutive output pixels = BH full image rows (W in {8, 16, 32});  ONE cp.async.bulk.tensor box
+//     [W][BH rows][channels][1 image] per vertical tap lands the rows y0+dy .. of ALL channels of the shifted tensor in
+//     shared memory (the vertical shift is a coordinate, top / bottom padding is TMA's zero fill), one more box the
+//     other tensor: 3 x 1.5 KB + 6 KB per k-block for a DenseNet3 bottleneck 3x3 instead of 20 KB of per-thread loads,
+//     issued up to NR k-blocks ahead by one producer thread;
+//   * the three horizontal taps read the same box at a shared-memory offset of -1 / 0 / +1 pixel (aligned 128-bit
+//     load + one scalar for the element that crosses the 16-byte boundary, left / right padding is a mask);
+//   * two teams of 128 transform threads take alternate k-blocks: raw box -> registers -> hi / lo split -> the
+//     canonical K-major SWIZZLE_128B operand layout (a 32-pixel row is exactly one 128-byte swizzle row, so the raw
+//     reads -- 8 lanes = 128 contiguous bytes -- and the swizzled 128-bit stores are both bank-conflict free);
+//   * SS-form tcgen05.mma from the swizzled stages, accumulators drained every WT_G k-blocks, fp32 atomics into the
+//     flat gradient vector: unchanged.
+//
+// Eligible: stride 1, "same" size, W in {8, 16, 32} with H*W a multiple of 32, horizontal shift in {-1, 0, +1}, and either
+// a 1x1 kernel or all taps of the shifted tensor in one 128-row tile (taps x channels <= 128; for a "same" convolution
+// the tensor with fewer channels is the shifted one, as in conv_tc_wgrad.cu).  Everything else: conv_tc_wgrad.cu.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "conv_args.h"
+#include "tc_common.cuh"
+#include "tma_common.h"
+
+namespace b2s {
+
+constexpr int WT_THREADS = 512;
+constexpr int WT_NST = 3;                      // operand stages (swizzled hi / lo images)
+constexpr int WT_G = 4;                        // k-blocks accumulated in TMEM between drains (see conv_tc_wgrad.cu)
+constexpr int WT_WARP_MMA = 12;
+constexpr int WT_WARP_TMA = 13;
+constexpr uint32_t WT_A_BYTES = TC_M * 128;    // 128 rows x 32 pixels of fp32: one of hi / lo, also the raw A area
+
+template <int BN>
+struct WtSmem {
+    static constexpr int NR = BN <= 48 ? 4 : 3;                               // raw stages
+    static constexpr uint32_t B_BYTES = BN * 128;
+    static constexpr uint32_t STAGE_BYTES = 2 * WT_A_BYTES + 2 * B_BYTES;     // A hi | A lo | B hi | B lo
+    static constexpr uint32_t RAW_BYTES = WT_A_BYTES + B_BYTES;               // raw A boxes | raw B box
+    static constexpr size_t BYTES = (size_t)WT_NST * STAGE_BYTES + (size_t)NR * RAW_BYTES + 256 + 1024;
+};
+
+struct alignas(64) WtMaps {
+    CUtensorMap a[kMaxPairs];                  // shifted tensor of every pair
+    CUtensorMap b[kMaxPairs];                  // the other tensor
+};
+
+struct WtGeom {
+    int mtiles, ntiles, ksplit, swapped;
+    int BH;                                    // image rows per k-block: W * BH = 32
+    int ndy;                                   // vertical taps = boxes of the shifted tensor per k-block (1 for a 1x1 kernel)
+    int boxCa;                                 // channels per box of the shifted tensor
+};
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row atoms 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                    // leading byte offset: unused for swizzled K-major layouts
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                    // version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+
+// debug timeline (compiled in only with -DB2S_TC_TRACE_ENABLED): trace[(role * WT_TRACE_IT + i) * 4 + slot] = clock64() of CTA 0
+constexpr int WT_TRACE_IT = 72;
+__device__ __forceinline__ void wt_stamp(long long* trace, int role, int i, int slot) {
+#ifdef B2S_TC_TRACE_ENABLED
+    if (trace && blockIdx.x == 0 && i < WT_TRACE_IT) trace[((size_t)role * WT_TRACE_IT + i) * 4 + slot] = clock64();
+#else
+    (void)trace; (void)role; (void)i; (void)slot;
+#endif
+}
+
+__device__ __forceinline__ float wt_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void wt_split_store(uint8_t* hi_img, uint8_t* lo_img, const uint32_t off, const float4 v) {
+    float4 hi, lo;
+    hi.x = wt_hi(v.x); lo.x = v.x - hi.x;
+    hi.y = wt_hi(v.y); lo.y = v.y - hi.y;
+    hi.z = wt_hi(v.z); lo.z = v.z - hi.z;
+    hi.w = wt_hi(v.w); lo.w = v.w - hi.w;
+    *reinterpret_cast<float4*>(hi_img + off) = hi;
+    *reinterpret_cast<float4*>(lo_img + off) = lo;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WT_THREADS, 1)
+conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, const WtGeom wg) {
+    extern __shared__ uint8_t wt_smem_raw[];
+    using S = WtSmem<BN>;
+    uint8_t* smem = wt_smem_raw + ((1024u - (smem_u32(wt_smem_raw) & 1023u)) & 1023u);      // swizzle atoms: 1024-byte aligned
+    uint8_t* stages = smem;
+    uint8_t* raws = smem + (size_t)WT_NST * S::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raws + (size_t)S::NR * S::RAW_BYTES);
+    uint64_t* raw_full = bars;                     // [NR]  TMA boxes landed (expect_tx)
+    uint64_t* raw_free = raw_full + S::NR;         // [NR]  the 4 warps of the team that owns the k-block have read it (one arrival per warp)
+    uint64_t* ab_full = raw_free + S::NR;          // [NST] the 4 warps of the owning team
+    uint64_t* ab_free = ab_full + WT_NST;          // [NST] tcgen05.commit
+    uint64_t* d_full = ab_free + WT_NST;           // [2]
+    uint64_t* d_empty = d_full + 2;                // [2]   the 4 drain warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+    const ConvGeom& g = a.g;
+    const int KHW = g.KH * g.KW;
+    const int HW = g.H * g.W;
+    const int W = g.W;
+    const int nkb = (int)(((long long)g.batch * HW) / TC_KB);
+    const int Mrows = KHW * g.Cin;
+    const bool one = KHW == 1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mt = blockIdx.x % wg.mtiles;
+    const int nt = (blockIdx.x / wg.mtiles) % wg.ntiles;
+    const int ksl = blockIdx.x / (wg.mtiles * wg.ntiles);
+    const int per = (nkb + wg.ksplit - 1) / wg.ksplit;
+    const int kb0 = ksl * per;
+    const int nloc = max(0, min(nkb, kb0 + per) - kb0);         // k-blocks of this CTA per pair
+    const int total = a.npairs * nloc;
+    const int rows_here = min(TC_M, Mrows - mt * TC_M);         // valid A rows of this tile
+
+    if (tid == 0) wt_stamp(a.trace, 3, WT_TRACE_IT - 1, 2);
+    // the producer thread initialises its own barriers and requests the first NR k-blocks at once: their flight overlaps
+    // the rest of the prologue (TMEM allocation, row table, zero fill) -- the timeline showed the first box landing
+    // ~1700 clocks after a request that was only issued behind the block-wide barrier
+    const uint32_t a_box = (uint32_t)wg.boxCa * 128u, b_box = (uint32_t)BN * 128u;
+    auto request = [&](const int i) {
+        const int p = i / nloc;
+        const int kb = kb0 + (i - p * nloc);
+        const int rs = i % S::NR;
+        const int j0 = kb * TC_KB;
+        const int n = j0 / HW;
+        const int y0 = (j0 - n * HW) / W;
+        uint8_t* dst = raws + (size_t)rs * S::RAW_BYTES;
+        mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)wg.ndy * a_box + b_box);
+        for (int d = 0; d < wg.ndy; ++d)
+            tma_load_4d(dst + (size_t)d * a_box, &maps.a[p], 0, one ? y0 : y0 + d - g.ph, one ? mt * TC_M : 0, n, &raw_full[rs]);
+        tma_load_4d(dst + WT_A_BYTES, &maps.b[p], 0, y0, nt * BN, n, &raw_full[rs]);
+    };
+    const int prefill = min(S::NR, total);
+    if (warp == WT_WARP_TMA && lane == 0) {
+        for (int s = 0; s < S::NR; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_free[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < prefill; ++i) request(i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < WT_NST; ++s) {
+            mbar_init(&ab_full[s], 4);
+            mbar_init(&ab_free[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d_full[b], 1);
+            mbar_init(&d_empty[b], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WT_WARP_MMA) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // per-row constants of the A tile, decoded once per row (the divisions cost ~2400 clocks when every transform thread
+    // did them for its eight rows): (raw float offset of the row's channel inside the boxes) * 4 + (dx + 1), -1 = no row
+    __shared__ int row_tab[TC_M];
+    if (tid < TC_M) {
+        const int m = mt * TC_M + tid;
+        int e = -1;
+        if (m < Mrows) {
+            if (one) e = (tid * 32) * 4 + 1;
+            else {
+                const int t = m / g.Cin, ca = m - t * g.Cin;
+                const int ky = t / g.KW, kx = t - ky * g.KW;
+                e = ((ky * wg.boxCa + ca) * 32) * 4 + (kx - g.pw + 1);
+            }
+        }
+        row_tab[tid] = e;
+    }
+    if (rows_here < TC_M) {   // A rows past the last valid one are never written: zero the stages once
+        float4* z = reinterpret_cast<float4*>(stages);
+        const int n4 = WT_NST * (int)S::STAGE_BYTES / 16;
+        for (int i = tid; i < n4; i += WT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ===================== transform: raw boxes -> registers (shift, split) -> swizzled operand stage =========
+        const int team = warp >> 2;
+        const int r = tid & 127;
+        const int kg = r & 7;                                   // 4-pixel group inside the k-block
+        const int rowsub = r >> 3;                              // rows rowsub + 16 q
+        const int x0 = (kg * 4) % W;
+        // per-row constants: raw offset (floats), horizontal shift, validity; swizzled destination offset (bytes)
+        int aoff[8], adx[8];
+        uint32_t doff[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int rl = rowsub + 16 * q;
+            doff[q] = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((kg ^ (rl & 7)) << 4));
+            const int e = row_tab[rl];
+            aoff[q] = e < 0 ? -1 : (e >> 2) + kg * 4;
+            adx[q] = e < 0 ? 0 : (e & 3) - 1;
+        }
+        const bool has_l = x0 > 0, has_r = x0 + 4 < W;
+        constexpr int NB = BN / 16;
+        for (int i = team; i < total; i += 2) {
+            const int rs = i % S::NR;
+            const int s = i % WT_NST;
+            const uint32_t round = i / WT_NST;
+            const float* __restrict__ rawA = reinterpret_cast<const float*>(raws + (size_t)rs * S::RAW_BYTES);
+            const float* __restrict__ rawB = rawA + WT_A_BYTES / 4;
+            if (r == 0) wt_stamp(a.trace, team, i, 0);
+            mbar_wait(&raw_full[rs], (i / S::NR) & 1);
+            if (r == 0) wt_stamp(a.trace, team, i, 1);
+            float4 ca[8];
+            float4 cb[NB];
+            float el[8], er[8];
+            // every load first (branch-free: a warp holds rows of different taps), then the shift as selects
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (16 * q >= rows_here) continue;              // block-uniform
+                const bool ok = aoff[q] >= 0;
+                const float* __restrict__ src = rawA + (ok ? aoff[q] : 0);
+                ca[q] = ok ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                el[q] = (ok && adx[q] < 0 && has_l) ? src[-1] : 0.f;
+                er[q] = (ok && adx[q] > 0 && has_r) ? src[4] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) cb[u] = *reinterpret_cast<const float4*>(rawB + (rowsub + 16 * u) * 32 + kg * 4);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (16 * q >= rows_here) continue;
+                const float4 v = ca[q];
+                if (adx[q] < 0) ca[q] = make_float4(el[q], v.x, v.y, v.z);
+                else if (adx[q] > 0) ca[q] = make_float4(v.y, v.z, v.w, er[q]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_free[rs]);          // the boxes are in registers: the producer may refill the stage
+            if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
+            __syncwarp();
+            if (r == 0) wt_stamp(a.trace, team, i, 2);
+            uint8_t* Ahi = stages + (size_t)s * S::STAGE_BYTES;
+            uint8_t* Alo = Ahi + WT_A_BYTES;
+            uint8_t* Bhi = Alo + WT_A_BYTES;
+            uint8_t* Blo = Bhi + S::B_BYTES;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (16 * q >= rows_here) continue;
+                wt_split_store(Ahi, Alo, doff[q], ca[q]);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) wt_split_store(Bhi, Blo, doff[u], cb[u]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ab_full[s]);
+            if (r == 0) wt_stamp(a.trace, team, i, 3);
+        }
+    } else if (warp < 12) {
+        // ===================== drain + epilogue (as conv_tc_wgrad.cu) =================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_DRAIN));
+        const int q = warp - 8;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        constexpr int NACC = tc_nacc(BN) > 3 ? 3 : tc_nacc(BN);
+        float acc[BN];
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+        uint32_t grp = 0;
+        for (int p = 0; p < a.npairs; ++p) {
+            const float sc = a.scale[p];
+            for (int k0 = 0; k0 < nloc; k0 += WT_G, ++grp) {
+                const int b = grp & 1;
+                if (r == 0) wt_stamp(a.trace, 3, (int)grp, 0);
+                mbar_wait(&d_full[b], (grp >> 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+                if (r == 0) wt_stamp(a.trace, 3, (int)grp, 1);
+                const uint32_t d0 = lane_addr + TC_DCOL0 + b * TC_DCOLS;
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[NACC][16];
+#pragma unroll
+                    for (int q2 = 0; q2 < NACC; ++q2) tmem_ld16(d0 + q2 * BN + c0, v[q2]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float d;
+                        if (NACC >= 3) d = (__uint_as_float(v[0][e]) + __uint_as_float(v[2][e])) + __uint_as_float(v[1][e]);
+                        else if (NACC == 2) d = __uint_as_float(v[1][e]) + __uint_as_float(v[0][e]);
+                        else d = __uint_as_float(v[0][e]);
+                        acc[c0 + e] = fmaf(d, sc, acc[c0 + e]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[b]);
+                if (r == 0) wt_stamp(a.trace, 3, (int)grp, 2);
+            }
+        }
+        if (r == 0) wt_stamp(a.trace, 3, WT_TRACE_IT - 1, 0);
+        const int m = mt * TC_M + r;
+        if (total > 0 && m < Mrows) {
+            const int t = m / g.Cin, ci = m - t * g.Cin;
+            if (!wg.swapped) {
+                // row = (tap, input channel), column = output channel:  Wbar[co][ci][t]
+                float* __restrict__ wrow = a.out + (long long)ci * KHW + t;
+#pragma unroll
+                for (int i = 0; i < BN; ++i) {
+                    const int co = nt * BN + i;
+                    if (co < g.Cout) atomicAdd(wrow + (long long)co * g.Cin * KHW, acc[i]);
+                }
+            } else {
+                // operands were exchanged (launcher): row = (mirrored tap, OUTPUT channel), column = INPUT channel;
+                // g.Cin is the layer's Cout and g.Cout its Cin here
+                float* __restrict__ wrow = a.out + (long long)ci * g.Cout * KHW + (KHW - 1 - t);
+#pragma unroll
+                for (int i = 0; i < BN; ++i) {
+                    const int c2 = nt * BN + i;
+                    if (c2 < g.Cout) atomicAdd(wrow + (long long)c2 * KHW, acc[i]);
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_MISC));
+        if (warp == WT_WARP_MMA) {
+            // ===================== MMA issuer ======================================================
+            const uint32_t idesc = umma_idesc_tf32(TC_M, BN);
+            const uint32_t idesc2 = umma_idesc_tf32(TC_M, 2 * BN <= 256 ? 2 * BN : BN);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint64_t desc0 = umma_desc_sw128(smem_u32(stages));            // stage 0, A hi, k-step 0
+            constexpr int NACC = tc_nacc(BN) > 3 ? 3 : tc_nacc(BN);
+            constexpr uint32_t STAGE16 = S::STAGE_BYTES >> 4, A16 = WT_A_BYTES >> 4, B16 = S::B_BYTES >> 4;
+            uint32_t grp = 0;
+            for (int i = 0; i < total; ++i) {
+                const int s = i % WT_NST;
+                const uint32_t round = i / WT_NST;
+                const int kk = i % nloc;                              // k-block inside its pair: drain groups never span pairs
+                const bool first = (kk % WT_G) == 0;
+                const bool last = (kk % WT_G) == WT_G - 1 || kk == nloc - 1;
+                const int b = grp & 1;
+                const uint32_t use = grp >> 1;
+                if (lane == 0) wt_stamp(a.trace, 2, i, 0);
+                mbar_wait(&ab_full[s], round & 1);
+                if (lane == 0) wt_stamp(a.trace, 2, i, 1);
+                if (first && use > 0) mbar_wait(&d_empty[b], (use - 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+                if (lane == 0) wt_stamp(a.trace, 2, i, 2);
+                const uint32_t d_addr = tmem_u + TC_DCOL0 + b * TC_DCOLS;
+                const uint64_t dAh = desc0 + (uint64_t)(s * STAGE16), dAl = dAh + A16;
+                const uint64_t dBh = dAl + A16, dBl = dBh + B16;
+                const uint32_t cont = first ? 0u : 1u;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < TC_KB / 8; ++ks) {
+                        const uint64_t ko = (uint64_t)(ks * 2);           // 32 bytes per k-step inside the 128-byte swizzle row
+                        const uint32_t accf = ks >= 1 ? 1u : cont;
+                        if (NACC == 3) {
+                            umma_tf32_ss(d_addr + BN, dAh + ko, dBh + ko, idesc2, accf);      // [hi*hi | hi*lo]
+                            umma_tf32_ss(d_addr, dAl + ko, dBh + ko, idesc, accf);            // lo*hi
+                        } else if (NACC == 2) {
+                            umma_tf32_ss(d_addr, dAh + ko, dBh + ko, idesc2, accf);
+                            umma_tf32_ss(d_addr + BN, dAl + ko, dBh + ko, idesc, 1u);
+                        } else {
+                            umma_tf32_ss(d_addr, dAh + ko, dBl + ko, idesc, accf);
+                            umma_tf32_ss(d_addr, dAl + ko, dBh + ko, idesc, 1u);
+                            umma_tf32_ss(d_addr, dAh + ko, dBh + ko, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&ab_free[s]);
+                    if (last) umma_commit(&d_full[b]);
+                }
+                __syncwarp();
+                if (lane == 0) wt_stamp(a.trace, 2, i, 3);
+                if (last) ++grp;
+            }
+        } else if (warp == WT_WARP_TMA) {
+            // ===================== producer: the boxes of a k-block, NR k-blocks ahead ===============
+            for (int i = prefill; i < total; ++i) {
+                if (lane == 0) {
+                    mbar_wait(&raw_free[i % S::NR], ((uint32_t)(i / S::NR) - 1) & 1);
+                    request(i);
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    if (tid == 256) wt_stamp(a.trace, 3, WT_TRACE_IT - 1, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WT_WARP_MMA) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+template <int BN>
+static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, const WtGeom& wg) {
+    constexpr size_t smem = WtSmem<BN>::BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv_wgrad_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+        attr_set = true;
+    }
+    static const bool want_trace = getenv("B2S_WG_TRACE") != nullptr;
+    static int traced = 0;
+    if (want_trace && traced < 6 && a.g.KH == (getenv("B2S_WG_TRACE_K") ? atoi(getenv("B2S_WG_TRACE_K")) : 3)) {   // debug: synchronous launch + timeline of CTA 0
+        ++traced;
+        long long* d_tr = nullptr;
+        const size_t n = 4 * WT_TRACE_IT * 4;
+        cudaMalloc(&d_tr, n * sizeof(long long));
+        cudaMemset(d_tr, 0, n * sizeof(long long));
+        ConvKArgs b = a;
+        b.trace = d_tr;
+        conv_wgrad_tma_kernel<BN><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(b, maps, wg);
+        cudaStreamSynchronize(st);
+        std::vector<long long> h(n);
+        cudaMemcpy(h.data(), d_tr, n * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(d_tr);
+        auto raw = [&](int role, int i, int slot) { return h[((size_t)role * WT_TRACE_IT + i) * 4 + slot]; };
+        const long long t0 = raw(3, WT_TRACE_IT - 1, 2);
+        auto at = [&](int role, int i, int slot) { const long long v = raw(role, i, slot); return v ? v - t0 : -1; };
+        fprintf(stderr, "WGT trace BN=%d Cin=%d Cout=%d k=%d W=%d grid=%d (clocks since kernel start); drain loop end %lld, epilogue end %lld\n", BN,
+                a.g.Cin, a.g.Cout, a.g.KH, a.g.W, wg.mtiles * wg.ntiles * wg.ksplit, at(3, WT_TRACE_IT - 1, 0), at(3, WT_TRACE_IT - 1, 1));
+        for (int i = 0; i < WT_TRACE_IT - 1; ++i) {
+            const int team = i & 1;
+            if (at(2, i, 0) < 0) break;
+            fprintf(stderr, "  it %2d  X%d: poll %6lld raw_ok %6lld ab_free %6lld stored %6lld | MMA: poll %6lld ab_ok %6lld d_ok %6lld issued %6lld | D[%d]: poll %6lld full %6lld done %6lld\n",
+                    i, team, at(team, i, 0), at(team, i, 1), at(team, i, 2), at(team, i, 3), at(2, i, 0), at(2, i, 1), at(2, i, 2), at(2, i, 3),
+                    i / WT_G, at(3, i / WT_G, 0), at(3, i / WT_G, 1), at(3, i / WT_G, 2));
+        }
+        return 1;
+    }
+    conv_wgrad_tma_kernel<BN><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(a, maps, wg);
+    return 1;
+}
+
+// Returns 1 when the kernel was launched, 0 when the layer is not eligible, <0 on error.
+int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
+    static const int enabled = getenv("B2S_WGRAD_TMA") ? atoi(getenv("B2S_WGRAD_TMA")) : 1;
+    const int mode = get_tc_mode();
+    if (!enabled || mode == 0) return 0;
+    ConvKArgs a = a0;
+    ConvGeom& g = a.g;
+    const long long J = (long long)g.batch * g.OH * g.OW;
+    if (g.sh != 1 || g.sw != 1 || g.H != g.OH || g.W != g.OW) return 0;
+    if (g.W != 8 && g.W != 16 && g.W != 32) return 0;
+    const int BH = TC_KB / g.W;
+    if (g.H % BH != 0 || J >= (1LL << 31)) return 0;
+    if (g.pw > 1 || g.KW - 1 - g.pw > 1) return 0;
+    if ((g.in_sstride & 3) || (g.out_sstride & 3) || ((uintptr_t)a.out & 3)) return 0;
+    for (int p = 0; p < a.npairs; ++p)
+        if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) return 0;
+    if (mode == 1 && !tc_worth_it(J, g.Cin, g.Cout, g.KH * g.KW)) return 0;
+    const int KHW = g.KH * g.KW;
+    // which tensor is shifted (A rows = taps x its channels): for a "same" convolution the sum over output pixels of
+    // g[co,px] x[ci,px+s] equals the sum over input pixels of x[ci,px'] g[co,px'-s] -- exchange the operands, mirror the
+    // taps.  k x k: the tensor with fewer channels (all its taps must fit one 128-row tile); 1x1: the one with MORE
+    // channels supplies the rows, the other one the (narrow) columns.
+    const bool same = 2 * g.ph == g.KH - 1 && 2 * g.pw == g.KW - 1;
+    int swapped = 0;
+    if (same && (KHW > 1 ? g.Cout < g.Cin : g.Cout > g.Cin)) {
+        swapped = 1;
+        for (int p = 0; p < a.npairs; ++p) std::swap(a.act[p], a.wt[p]);
+        std::swap(g.Cin, g.Cout);
+        std::swap(g.in_sstride, g.out_sstride);
+    }
+    if (KHW > 1 && KHW * g.Cin > TC_M) return 0;
+    const int BN = tc_choose_bn(g.Cout);
+    if (BN > 64) return 0;
+    TmEncodeFn enc = tm_encoder();
+    if (!enc) return 0;
+    WtGeom wg;
+    wg.swapped = swapped;
+    wg.BH = BH;
+    wg.ndy = KHW == 1 ? 1 : g.KH;
+    wg.boxCa = KHW == 1 ? std::min(TC_M, (g.Cin + 7) & ~7) : g.Cin;
+    if ((long long)wg.ndy * wg.boxCa * 128 > (long long)WT_A_BYTES) return 0;
+    wg.mtiles = (KHW * g.Cin + TC_M - 1) / TC_M;
+    wg.ntiles = (g.Cout + BN - 1) / BN;
+    const int nkb = (int)(J / TC_KB);
+    static const int min_kb = getenv("B2S_WGT_MINKB") ? std::max(1, atoi(getenv("B2S_WGT_MINKB"))) : 16;
+    static const int max_ctas = getenv("B2S_WG_MAXCTAS") ? std::max(1, atoi(getenv("B2S_WG_MAXCTAS"))) : kNumSMs;
+    int ksplit = std::max(1, max_ctas / (wg.mtiles * wg.ntiles));
+    ksplit = std::min(ksplit, std::max(1, nkb / min_kb));
+    wg.ksplit = ksplit;
+    WtMaps maps;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int p = 0; p < a.npairs; ++p) {
+        for (int which = 0; which < 2; ++which) {
+            const float* base = which == 0 ? a.act[p] : a.wt[p];
+            const int C = which == 0 ? g.Cin : g.Cout;
+            const long long ss = which == 0 ? g.in_sstride : g.out_sstride;
+            const cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)C, (cuuint64_t)g.batch};
+            const cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)ss * 4};
+            const cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)BH, (cuuint32_t)(which == 0 ? wg.boxCa : BN), 1};
+            const CUresult r = enc(which == 0 ? &maps.a[p] : &maps.b[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims,
+                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return 0;
+        }
+    }
+    for (int p = a.npairs; p < kMaxPairs; ++p) { maps.a[p] = maps.a[0]; maps.b[p] = maps.b[0]; }
+    switch (BN) {
+    case 16: return launch_wt_t<16>(st, a, maps, wg);
+    case 32: return launch_wt_t<32>(st, a, maps, wg);
+    case 48: return launch_wt_t<48>(st, a, maps, wg);
+    default: return launch_wt_t<64>(st, a, maps, wg);
+    }
+}
+
+}  // namespace b2s

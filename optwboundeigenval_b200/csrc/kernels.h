@@ -86,8 +86,8 @@ struct BnArgs {
     double* csum;             // third-order compatibility sweep: [bn_corr_sums()][C]
     const struct PeerCtx* peer;   // multi-GPU: exchange context for the in-kernel all-reduce of the sums (peer.cuh), else NULL
     const struct PeerCtx* peer_tail;   // multi-GPU: the statistics kernels' last block all-reduces the sums, else NULL
-    int peer_ll;              // with peer: 1 = per-channel packet exchange, no grid barrier (peer_exchange_channel); 0 = block 0
-                              // exchanges between two grid barriers
+    int peer_ll;              // with peer: 1 = per-channel packet exchange, no grid barrier (peer_exchange_channel); 2 = its
+                              // single-GPU form (per-channel barrier); 0 = block 0 exchanges between two grid barriers
 };
 int launch_bn_fwd_stats(cudaStream_t st, int order, const BnArgs& a);
 int launch_bn_fwd_apply(cudaStream_t st, int order, const BnArgs& a);

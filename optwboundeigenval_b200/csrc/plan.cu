@@ -189,6 +189,7 @@ struct b2s_plan {
 
     b2s_pistate* pi = nullptr;
     Comm* comm = nullptr;
+    LocalPeer* local_peer = nullptr;  // single GPU: per-channel barrier of the fused BatchNorm kernels (B2S_BN_CHANSYNC)
     int world = 1;
     long long global_batch = 0;       // samples over all ranks of the cached base pass (0: batch * world)
 
@@ -280,6 +281,7 @@ static BnArgs bn_args(b2s_plan* p, int oi, int K) {
     a.peer = (p->comm && 2 * a.C <= 4096) ? comm_peer_ctx(p->comm) : nullptr;
     a.peer_tail = (p->comm && 2 * a.C <= 4096) ? comm_peer_tail_ctx(p->comm) : nullptr;
     a.peer_ll = (a.peer && comm_peer_ll(p->comm)) ? 1 : 0;
+    if (!p->comm && p->local_peer && 2 * a.C <= 4096) { a.peer = local_peer_ctx(p->local_peer); a.peer_ll = 2; }
     return a;
 }
 
@@ -804,6 +806,10 @@ int b2s_plan_create(const b2s_tensor* tensors, int32_t n_tensors, const int64_t*
     p->device = device;
     if (const char* e = getenv("B2S_BN_FUSED")) p->bn_fused = atoi(e) != 0;      // experiment switch
     if (const char* e = getenv("B2S_WGRAD_SIDE")) p->wgrad_side = atoi(e) != 0;
+    {
+        const char* e = getenv("B2S_BN_CHANSYNC");
+        if (e && atoi(e) != 0 && local_peer_create(&p->local_peer) != 0) { delete p; return -2; }
+    }
     p->tensors.assign(tensors, tensors + n_tensors);
     p->ops.assign(ops, ops + n_ops);
     p->buf_elems.assign(buf_elems, buf_elems + n_bufs);
@@ -964,6 +970,7 @@ int b2s_plan_destroy(b2s_plan* p) {
     cudaFree(p->labels); cudaFree(p->target); cudaFree(p->coef);
     if (p->pi) b2s_pi_destroy(p->pi);
     if (p->comm) comm_destroy(p->comm);
+    local_peer_destroy(p->local_peer);
     for (int i = 0; i < b2s_plan::kMaxSide; ++i) {
         if (p->sides[i]) { cudaStreamSynchronize(p->sides[i]); cudaStreamDestroy(p->sides[i]); }
         if (p->ev_joins[i]) cudaEventDestroy(p->ev_joins[i]);
