@@ -19,7 +19,8 @@ T="python tools/ncu_target.py cifar_densenet 32 2"
 $T > gpurun_out/${R}_target_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:conv_tma_kernel -s 158 -c 4 -o $REP/${R}_conv_tma -f $T > gpurun_out/${R}_ncu_conv_tma.log 2>&1
 echo "conv_tma rc $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_wgrad_kernel -s 80 -c 2 -o $REP/${R}_conv_wgrad -f $T > gpurun_out/${R}_ncu_wgrad.log 2>&1
+# DenseNet3's weight gradients run on conv_wgrad_tma_kernel (conv_wgrad_tma.cu): launches 62.. are block-1 layers of the Hv pass
+ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_tma_kernel -s 62 -c 4 -o $REP/${R}_conv_wgrad -f $T > gpurun_out/${R}_ncu_wgrad.log 2>&1
 echo "wgrad rc $?"
 ncu --set full --clock-control none -k regex:bn_ -s 160 -c 2 -o $REP/${R}_bn -f $T > gpurun_out/${R}_ncu_bn.log 2>&1
 echo "bn rc $?"
