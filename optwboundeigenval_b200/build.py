@@ -26,6 +26,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 if os.environ.get("B2S_BUILD_TRUNC"):          # experiment: truncating TF32 split in conv_tma.cu
     CFLAGS.append("-DB2S_TMA_TRUNC")
+if os.environ.get("B2S_BUILD_TM_G"):           # experiment: k-blocks per drain group in conv_tma.cu
+    CFLAGS.append("-DB2S_TM_G=" + os.environ["B2S_BUILD_TM_G"])
 if os.environ.get("B2S_BUILD_TRACE"):          # per-role clock stamps in the tcgen05 kernel (tools/tc_trace.py)
     CFLAGS.append("-DB2S_TC_TRACE_ENABLED")
 

@@ -45,7 +45,10 @@ constexpr int TM_WARP_B = 13;
 constexpr int TM_WARP_RAW = 14;
 constexpr int TM_NR = 4;                               // raw activation stages (TMA boxes of <= 16 KB)
 constexpr int TM_RAW_FLOATS = TC_M * TC_KB;            // floats reserved per raw stage
-constexpr int TM_G = 4;                                // k-blocks accumulated in TMEM between drains
+#ifndef B2S_TM_G
+#define B2S_TM_G 4
+#endif
+constexpr int TM_G = B2S_TM_G;                         // k-blocks accumulated in TMEM between drains
 
 struct alignas(64) TmaMaps { CUtensorMap m[kMaxPairs]; };
 

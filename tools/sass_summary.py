@@ -25,7 +25,7 @@ def main():
         name = names.get(mangled, mangled)
         if not any(k + "<" in name for k in KERNELS):
             continue
-        ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", block, flags=re.M)
+        ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", block, flags=re.M)
         cnt = collections.Counter()
         variants = set()
         for op in ops:
