@@ -399,6 +399,257 @@ __global__ void __launch_bounds__(1024) bn_bwd_chan_kernel(const BnArgs a, float
     __syncthreads();
     bn_bwd_apply_body<K, VEC>(a, ps);
 }
+// ---- one CTA per channel, the channel's operands cached in shared memory ---------------------------------
+// The per-launch timeline of the DenseNet3 HVP showed a floor of 12.7 us per BatchNorm launch in block 3 (100 K elements)
+// and 14.7 us in block 2: launch + TWO dependent trips to memory (statistics, then the same tensors again for the
+// apply phase) + the round trip of the sums through global memory (atomics, fence, read back by the thread that
+// derives the channel coefficients).  Here every tensor of the channel is read ONCE into a shared-memory cache
+// (float4 cache[slot][n], n = chunks of the channel; slots: x_0..x_K, then y0 for the ReLU mask, then g_0..g_K in the
+// adjoint kernel), both phases work from the cache, the block totals go straight from the reduction into the
+// coefficient computation (the sums are still stored for the later passes) and the lower orders' sums are fetched while
+// the cache fills.  128-bit path only; extents whose cache does not fit stay on the cooperative kernels.
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, long long idx) { return *reinterpret_cast<const float4*>(p + idx); }
+__device__ __forceinline__ float f4(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
+
+template <int K>
+__global__ void __launch_bounds__(1024) bn_fwd_chanc_kernel(const BnArgs a, int do_stats) {
+    extern __shared__ float4 bn_cache[];
+    __shared__ double red[64];
+    __shared__ BnChanRaw sch;
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x;
+    const unsigned Q = (unsigned)(a.HW / 4);
+    const unsigned n = (unsigned)a.batch * Q;
+    const long long coff = (long long)c * a.HW;
+    const bool mask = a.relu && K > 0;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned s = i / Q, q = i - s * Q;
+        const long long off = coff + (long long)q * 4;
+        const long long ii = (long long)s * a.in_sstride + off, oi = (long long)s * a.out_sstride + off;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) bn_cache[k * n + i] = a.x[k] ? ld4(a.x[k], ii) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mask) bn_cache[(K + 1) * n + i] = ld4(a.y0, oi);
+    }
+    // every thread reads back only what it wrote: no barrier between the fill and the statistics
+    double tot[2] = {0.0, 0.0};
+    if (do_stats) {
+        const double N = (double)a.count;
+        float mu0 = 0.f, mu1 = 0.f;
+        if (K >= 1) mu0 = (float)(a.fsum[0][0 * a.C + c] / N);
+        if (K >= 2) mu1 = (float)(a.fsum[1][0 * a.C + c] / N);
+        double T = 0, Qs = 0;
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+            const float4 v0 = bn_cache[i];
+            float4 v1 = v0, v2 = v0;
+            if (K >= 1) v1 = bn_cache[n + i];
+            if (K >= 2) v2 = bn_cache[2 * n + i];
+            float t = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x0 = f4(v0, e);
+                if (K == 0) {
+                    t += x0;
+                    Qs += (double)x0 * x0;
+                } else if (K == 1) {
+                    const float x1 = f4(v1, e);
+                    t += x1;
+                    Qs += 2.0 * (double)((x0 - mu0) * x1);
+                } else {
+                    const float x1 = f4(v1, e), x2 = f4(v2, e);
+                    const float c1 = x1 - mu1;
+                    t += x2;
+                    Qs += 2.0 * (double)(c1 * c1 + (x0 - mu0) * x2);
+                }
+            }
+            T += (double)t;
+        }
+        double v[2] = {T, Qs};
+        block_sum<2, double>(v, red);
+        if (threadIdx.x == 0) {           // single writer per channel: plain stores (the arena was zeroed for the atomics of the other forms)
+            a.fsum[K][0 * a.C + c] = v[0];
+            a.fsum[K][1 * a.C + c] = v[1];
+        }
+        tot[0] = v[0]; tot[1] = v[1];      // valid in thread 0
+        if (a.peer) peer_exchange_channel<2>(a.fsum[K], a.C, c, *a.peer, tot);     // data parallel: global sums, all threads
+    }
+    if (threadIdx.x == 0) {
+        const double* ovr = do_stats ? tot : nullptr;
+        to_raw<K>(bn_channel<K>(a, c, ovr), sch);
+        if (K == 0 && a.running_mean) {
+            const double N = (double)a.count;
+            const double mu = (ovr ? ovr[0] : a.fsum[0][0 * a.C + c]) / N;
+            double var = (ovr ? ovr[1] : a.fsum[0][1 * a.C + c]) / N - mu * mu;
+            if (var < 0) var = 0;
+            const double unb = N > 1 ? var * N / (N - 1) : var;
+            const double m = (double)a.momentum;
+            a.running_mean[c] = (float)((1.0 - m) * (double)a.running_mean[c] + m * mu);
+            a.running_var[c] = (float)((1.0 - m) * (double)a.running_var[c] + m * unb);
+        }
+    }
+    __syncthreads();
+    const BnChan<K> ch = from_raw<K>(sch);
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned s = i / Q, q = i - s * Q;
+        const long long oi = (long long)s * a.out_sstride + coff + (long long)q * 4;
+        const float4 v0 = bn_cache[i];
+        float4 v1 = v0, v2 = v0, m0 = v0;
+        if (K >= 1) v1 = bn_cache[n + i];
+        if (K >= 2) v2 = bn_cache[2 * n + i];
+        if (mask) m0 = bn_cache[(K + 1) * n + i];
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const Jet<K, float> xj(f4(v0, e), K >= 1 ? f4(v1, e) : 0.f, K >= 2 ? f4(v2, e) : 0.f);
+            const Jet<K, float> xh = (xj - ch.mu) * ch.r;
+            const Jet<K, float> y = ch.gam * xh + ch.bet;
+            float r = y.c[K];
+            if (a.relu) {
+                if (K == 0) r = r > 0.f ? r : 0.f;
+                else r = f4(m0, e) > 0.f ? r : 0.f;
+            }
+            o[e] = r;
+        }
+        *reinterpret_cast<float4*>(a.yk + oi) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(1024) bn_bwd_chanc_kernel(const BnArgs a, float pgrad_scale) {
+    extern __shared__ float4 bn_cache[];
+    __shared__ double red[64];
+    __shared__ BnChanRaw sch;
+    __shared__ float sm[2][3];
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x;
+    const unsigned Q = (unsigned)(a.HW / 4);
+    const unsigned n = (unsigned)a.batch * Q;
+    const long long coff = (long long)c * a.HW;
+    constexpr int SY = K + 1, SG = K + 2;          // slots: x_0..x_K | y0 | g_0..g_K
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned s = i / Q, q = i - s * Q;
+        const long long off = coff + (long long)q * 4;
+        const long long ii = (long long)s * a.in_sstride + off, oi = (long long)s * a.out_sstride + off;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+            bn_cache[k * n + i] = a.x[k] ? ld4(a.x[k], ii) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bn_cache[(SG + k) * n + i] = a.g[k] ? ld4(a.g[k], oi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (a.relu) bn_cache[SY * n + i] = ld4(a.y0, oi);
+    }
+    if (threadIdx.x == 0) to_raw<K>(bn_channel<K>(a, c), sch);      // forward sums of all orders are final
+    __syncthreads();
+    const BnChan<K> ch = from_raw<K>(sch);
+    double G = 0, X = 0;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        float4 xv[3], gv[3], m0 = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int k = 0; k <= K; ++k) { xv[k] = bn_cache[k * n + i]; gv[k] = bn_cache[(SG + k) * n + i]; }
+        if (a.relu) m0 = bn_cache[SY * n + i];
+        float gs = 0.f, xs = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (a.relu && !(f4(m0, e) > 0.f)) continue;
+            const Jet<K, float> xj(f4(xv[0], e), K >= 1 ? f4(xv[1], e) : 0.f, K >= 2 ? f4(xv[2], e) : 0.f);
+            const Jet<K, float> ge(f4(gv[0], e), K >= 1 ? f4(gv[1], e) : 0.f, K >= 2 ? f4(gv[2], e) : 0.f);
+            const Jet<K, float> xh = (xj - ch.mu) * ch.r;
+            gs += ge.c[K];
+            xs += (ge * xh).c[K];
+        }
+        G += (double)gs;
+        X += (double)xs;
+    }
+    double v[2] = {G, X};
+    block_sum<2, double>(v, red);
+    if (threadIdx.x == 0) {
+        a.bsum[K][0 * a.C + c] = v[0];
+        a.bsum[K][1 * a.C + c] = v[1];
+    }
+    double tot[2] = {v[0], v[1]};                  // valid in thread 0
+    if (a.peer) peer_exchange_channel<2>(a.bsum[K], a.C, c, *a.peer, tot);
+    if (threadIdx.x == 0) {
+        const double N = (double)a.count;
+        Jet<K, float> Gj, Xj;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+            Gj.c[k] = (float)((k == K ? tot[0] : a.bsum[k][0 * a.C + c]) / N);
+            Xj.c[k] = (float)((k == K ? tot[1] : a.bsum[k][1 * a.C + c]) / N);
+        }
+        const Jet<K, float> t1 = ch.gam * Gj, t2 = ch.gam * Xj;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sm[0][k] = t1.c[k]; sm[1][k] = t2.c[k]; }
+        atomicAdd(a.out_beta + c, (float)(tot[0] * (double)pgrad_scale));
+        atomicAdd(a.out_gamma + c, (float)(tot[1] * (double)pgrad_scale));
+    }
+    __syncthreads();
+    if (a.xbar == nullptr) return;
+    Jet<K, float> m1, m2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m1.c[k] = sm[0][k]; m2.c[k] = sm[1][k]; }
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned s = i / Q, q = i - s * Q;
+        const long long ii = (long long)s * a.in_sstride + coff + (long long)q * 4;
+        float4 xv[3], gv[3], m0 = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int k = 0; k <= K; ++k) { xv[k] = bn_cache[k * n + i]; gv[k] = bn_cache[(SG + k) * n + i]; }
+        if (a.relu) m0 = bn_cache[SY * n + i];
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.accumulate) prev = ld4(a.xbar, ii);
+        float o[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const Jet<K, float> xj(f4(xv[0], e), K >= 1 ? f4(xv[1], e) : 0.f, K >= 2 ? f4(xv[2], e) : 0.f);
+            const Jet<K, float> xh = (xj - ch.mu) * ch.r;
+            Jet<K, float> ge;
+            if (!a.relu || f4(m0, e) > 0.f) ge = Jet<K, float>(f4(gv[0], e), K >= 1 ? f4(gv[1], e) : 0.f, K >= 2 ? f4(gv[2], e) : 0.f);
+            const Jet<K, float> u = ch.gam * ge - m1 - xh * m2;
+            const Jet<K, float> xb = ch.r * u;
+            o[e] += xb.c[K];
+        }
+        *reinterpret_cast<float4*>(a.xbar + ii) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// shared-memory bytes of the cached form, or 0 when it does not apply (128-bit path only; B2S_BN_CACHED=0 switches it off)
+static inline size_t bn_cached_smem(const BnArgs& a, int vec, int order, bool bwd) {
+    static const int on = getenv("B2S_BN_CACHED") ? atoi(getenv("B2S_BN_CACHED")) : 1;
+    if (!on || vec != 4 || a.C < 16 || (a.peer && !a.peer_ll)) return 0;
+    const size_t n = (size_t)a.batch * a.HW / 4;
+    const int slots = bwd ? 2 * (order + 1) + 1 : (order + 1) + 1;
+    const size_t bytes = n * slots * sizeof(float4);
+    return bytes <= 200 * 1024 ? bytes : 0;
+}
+static inline int bn_cached_block(const BnArgs& a) {
+    const size_t n = (size_t)a.batch * a.HW / 4;
+    return n >= 2048 ? 1024 : n >= 1024 ? 512 : 256;
+}
+template <int K>
+static int launch_chanc(cudaStream_t st, const BnArgs& a, bool bwd, size_t smem, int do_stats) {
+    static bool attr_f = false, attr_b = false;
+    if (!bwd && !attr_f) {
+        B2S_CUDA(cudaFuncSetAttribute(bn_fwd_chanc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_f = true;
+    }
+    if (bwd && !attr_b) {
+        B2S_CUDA(cudaFuncSetAttribute(bn_bwd_chanc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_b = true;
+    }
+    BnArgs b = a;
+    if (b.peer_ll == 2) { b.peer = nullptr; b.peer_ll = 0; }     // single GPU: one block per channel needs no barrier at all
+    const int blk = bn_cached_block(a);
+    cudaError_t e;
+    if (bwd) e = launch_pdl(bn_bwd_chanc_kernel<K>, dim3(a.C, 1), dim3(blk), smem, st, b, a.pgrad_scale);
+    else e = launch_pdl(bn_fwd_chanc_kernel<K>, dim3(a.C, 1), dim3(blk), smem, st, b, do_stats);
+    if (e != cudaSuccess) { set_error("cached BN launch: %s", cudaGetErrorString(e)); return -3; }
+    count_launch();
+    return 0;
+}
+static int launch_chanc_order(cudaStream_t st, int order, const BnArgs& a, bool bwd, size_t smem, int do_stats) {
+    return order == 0 ? launch_chanc<0>(st, a, bwd, smem, do_stats) : order == 1 ? launch_chanc<1>(st, a, bwd, smem, do_stats)
+                                                                                 : launch_chanc<2>(st, a, bwd, smem, do_stats);
+}
+
 // per-channel CTA form applies when a channel's extent is small enough for one CTA and there are enough
 // channels to occupy the machine; returns the block size or 0
 static inline int bn_chan_block(const BnArgs& a, int vec) {
@@ -468,6 +719,7 @@ int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stat
     ProfScope prof("bn_fwd_fused", 16.0 * elems, 4.0 * elems * (2 * order + 3), st);
     if (skip_family("bn_fwd")) return 0;
     const int vec = bn_vec(a);
+    if (const size_t smem = bn_cached_smem(a, vec, order, false)) return launch_chanc_order(st, order, a, false, smem, do_stats);
     if (const int blk = bn_chan_block(a, vec)) {
         BnArgs b = a;
         if (b.peer_ll == 2) { b.peer = nullptr; b.peer_ll = 0; }     // single GPU: one block per channel needs no barrier at all
@@ -487,6 +739,7 @@ int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     ProfScope prof("bn_bwd_fused", 16.0 * elems, 4.0 * elems * (4 * order + 7), st);
     if (skip_family("bn_bwd")) return 0;
     const int vec = bn_vec(a);
+    if (const size_t smem = bn_cached_smem(a, vec, order, true)) return launch_chanc_order(st, order, a, true, smem, 1);
     if (const int blk = bn_chan_block(a, vec)) {
         const float ps = a.pgrad_scale;
         BnArgs b = a;
