@@ -40,19 +40,28 @@
 namespace b2s {
 
 constexpr int WT_THREADS = 512;
-constexpr int WT_NST = 3;                      // operand stages (swizzled hi / lo images)
 constexpr int WT_G = 4;                        // k-blocks accumulated in TMEM between drains (see conv_tc_wgrad.cu)
 constexpr int WT_WARP_MMA = 12;
 constexpr int WT_WARP_TMA = 13;
 constexpr uint32_t WT_A_BYTES = TC_M * 128;    // 128 rows x 32 pixels of fp32: one of hi / lo, also the raw A area
 
-template <int BN>
+// FLAT = false: k-block = BH full image rows, 4D boxes [W][BH][C][1] (W in {8, 16, 32}).
+// FLAT = true : k-block = 32 consecutive pixels of the FLATTENED image plane (any W % 4 == 0: the 224 .. 28 wide maps of the
+//               chest models), 3D boxes [40][C][1] starting 4 pixels early (16-byte aligned; the vertical tap is an offset
+//               of dy * W pixels, planes are contiguous in NCHW, top / bottom padding is the zero fill outside the plane,
+//               a ragged last k-block of an image is zero-filled as well); the horizontal taps read the box at +-1 pixel
+//               and mask the pixels whose neighbour lies in the next image row.
+constexpr int WT_FLAT_ROW = 40;                // floats per raw row of the shifted tensor in FLAT mode (4 + 32 + 4)
+template <int BN, bool FLAT>
 struct WtSmem {
-    static constexpr int NR = BN <= 48 ? 4 : 3;                               // raw stages
+    static constexpr int NST = BN >= 96 ? 2 : 3;                              // operand stages
+    static constexpr int NR = FLAT ? 2 : (BN <= 48 ? 4 : 3);                  // raw stages
     static constexpr uint32_t B_BYTES = BN * 128;
     static constexpr uint32_t STAGE_BYTES = 2 * WT_A_BYTES + 2 * B_BYTES;     // A hi | A lo | B hi | B lo
-    static constexpr uint32_t RAW_BYTES = WT_A_BYTES + B_BYTES;               // raw A boxes | raw B box
-    static constexpr size_t BYTES = (size_t)WT_NST * STAGE_BYTES + (size_t)NR * RAW_BYTES + 256 + 1024;
+    static constexpr uint32_t RAW_A_BYTES = FLAT ? TC_M * WT_FLAT_ROW * 4 : WT_A_BYTES;
+    static constexpr uint32_t RAW_BYTES = RAW_A_BYTES + B_BYTES;              // raw A boxes | raw B box
+    static constexpr size_t BYTES = (size_t)NST * STAGE_BYTES + (size_t)NR * RAW_BYTES + 256 + 1024;
+    static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct alignas(64) WtMaps {
@@ -65,7 +74,18 @@ struct WtGeom {
     int BH;                                    // image rows per k-block: W * BH = 32
     int ndy;                                   // vertical taps = boxes of the shifted tensor per k-block (1 for a 1x1 kernel)
     int boxCa;                                 // channels per box of the shifted tensor
+    // FLAT mode: an m-tile = (vertical tap ky, channel group of G channels), rows = kx * G + channel
+    int G, ncg;                                // channels per group, groups
+    int kpi;                                   // k-blocks per image = ceil(H * W / 32)
 };
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row atoms 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -99,11 +119,12 @@ __device__ __forceinline__ void wt_split_store(uint8_t* hi_img, uint8_t* lo_img,
     *reinterpret_cast<float4*>(lo_img + off) = lo;
 }
 
-template <int BN>
+template <int BN, bool FLAT>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, const WtGeom wg) {
     extern __shared__ uint8_t wt_smem_raw[];
-    using S = WtSmem<BN>;
+    using S = WtSmem<BN, FLAT>;
+    constexpr int WT_NST = S::NST;
     uint8_t* smem = wt_smem_raw + ((1024u - (smem_u32(wt_smem_raw) & 1023u)) & 1023u);      // swizzle atoms: 1024-byte aligned
     uint8_t* stages = smem;
     uint8_t* raws = smem + (size_t)WT_NST * S::STAGE_BYTES;
@@ -120,7 +141,7 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
     const int KHW = g.KH * g.KW;
     const int HW = g.H * g.W;
     const int W = g.W;
-    const int nkb = (int)(((long long)g.batch * HW) / TC_KB);
+    const int nkb = FLAT ? g.batch * wg.kpi : (int)(((long long)g.batch * HW) / TC_KB);
     const int Mrows = KHW * g.Cin;
     const bool one = KHW == 1;
 
@@ -132,7 +153,10 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
     const int kb0 = ksl * per;
     const int nloc = max(0, min(nkb, kb0 + per) - kb0);         // k-blocks of this CTA per pair
     const int total = a.npairs * nloc;
-    const int rows_here = min(TC_M, Mrows - mt * TC_M);         // valid A rows of this tile
+    // FLAT: tile mt = (ky, channel group cg); its rows are kx * G + (channel - cg * G)
+    const int f_ky = FLAT ? mt / wg.ncg : 0, f_cg = FLAT ? mt - f_ky * wg.ncg : 0;
+    const int f_ch = FLAT ? min(wg.G, g.Cin - f_cg * wg.G) : 0;                    // channels of this group
+    const int rows_here = FLAT ? (g.KW - 1) * wg.G + f_ch : min(TC_M, Mrows - mt * TC_M);   // A rows of this tile (upper bound)
 
     if (tid == 0) wt_stamp(a.trace, 3, WT_TRACE_IT - 1, 2);
     // the producer thread initialises its own barriers and requests the first NR k-blocks at once: their flight overlaps
@@ -143,14 +167,22 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
         const int p = i / nloc;
         const int kb = kb0 + (i - p * nloc);
         const int rs = i % S::NR;
-        const int j0 = kb * TC_KB;
-        const int n = j0 / HW;
-        const int y0 = (j0 - n * HW) / W;
         uint8_t* dst = raws + (size_t)rs * S::RAW_BYTES;
-        mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)wg.ndy * a_box + b_box);
-        for (int d = 0; d < wg.ndy; ++d)
-            tma_load_4d(dst + (size_t)d * a_box, &maps.a[p], 0, one ? y0 : y0 + d - g.ph, one ? mt * TC_M : 0, n, &raw_full[rs]);
-        tma_load_4d(dst + WT_A_BYTES, &maps.b[p], 0, y0, nt * BN, n, &raw_full[rs]);
+        if (FLAT) {
+            const int n = kb / wg.kpi;
+            const int j0 = (kb - n * wg.kpi) * TC_KB;
+            mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)wg.G * (WT_FLAT_ROW * 4u) + b_box);
+            tma_load_3d(dst, &maps.a[p], j0 - 4 + (f_ky - g.ph) * W, f_cg * wg.G, n, &raw_full[rs]);
+            tma_load_3d(dst + S::RAW_A_BYTES, &maps.b[p], j0, nt * BN, n, &raw_full[rs]);
+        } else {
+            const int j0 = kb * TC_KB;
+            const int n = j0 / HW;
+            const int y0 = (j0 - n * HW) / W;
+            mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)wg.ndy * a_box + b_box);
+            for (int d = 0; d < wg.ndy; ++d)
+                tma_load_4d(dst + (size_t)d * a_box, &maps.a[p], 0, one ? y0 : y0 + d - g.ph, one ? mt * TC_M : 0, n, &raw_full[rs]);
+            tma_load_4d(dst + S::RAW_A_BYTES, &maps.b[p], 0, y0, nt * BN, n, &raw_full[rs]);
+        }
     };
     const int prefill = min(S::NR, total);
     if (warp == WT_WARP_TMA && lane == 0) {
@@ -182,14 +214,19 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
     // did them for its eight rows): (raw float offset of the row's channel inside the boxes) * 4 + (dx + 1), -1 = no row
     __shared__ int row_tab[TC_M];
     if (tid < TC_M) {
-        const int m = mt * TC_M + tid;
         int e = -1;
-        if (m < Mrows) {
-            if (one) e = (tid * 32) * 4 + 1;
-            else {
-                const int t = m / g.Cin, ca = m - t * g.Cin;
-                const int ky = t / g.KW, kx = t - ky * g.KW;
-                e = ((ky * wg.boxCa + ca) * 32) * 4 + (kx - g.pw + 1);
+        if (FLAT) {
+            const int kx = tid / wg.G, cl = tid - kx * wg.G;
+            if (kx < g.KW && cl < f_ch) e = (cl * WT_FLAT_ROW + 4) * 4 + (kx - g.pw + 1);
+        } else {
+            const int m = mt * TC_M + tid;
+            if (m < Mrows) {
+                if (one) e = (tid * 32) * 4 + 1;
+                else {
+                    const int t = m / g.Cin, ca = m - t * g.Cin;
+                    const int ky = t / g.KW, kx = t - ky * g.KW;
+                    e = ((ky * wg.boxCa + ca) * 32) * 4 + (kx - g.pw + 1);
+                }
             }
         }
         row_tab[tid] = e;
@@ -223,14 +260,20 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
             aoff[q] = e < 0 ? -1 : (e >> 2) + kg * 4;
             adx[q] = e < 0 ? 0 : (e & 3) - 1;
         }
-        const bool has_l = x0 > 0, has_r = x0 + 4 < W;
+        bool has_l = x0 > 0, has_r = x0 + 4 < W;
         constexpr int NB = BN / 16;
         for (int i = team; i < total; i += 2) {
             const int rs = i % S::NR;
             const int s = i % WT_NST;
             const uint32_t round = i / WT_NST;
             const float* __restrict__ rawA = reinterpret_cast<const float*>(raws + (size_t)rs * S::RAW_BYTES);
-            const float* __restrict__ rawB = rawA + WT_A_BYTES / 4;
+            const float* __restrict__ rawB = rawA + S::RAW_A_BYTES / 4;
+            if (FLAT) {                                         // column of this lane's 4-pixel group inside its image row
+                const int kb = kb0 + (i % nloc);
+                const int xx = ((kb % wg.kpi) * TC_KB + kg * 4) % W;
+                has_l = xx > 0;
+                has_r = xx + 4 < W;
+            }
             if (r == 0) wt_stamp(a.trace, team, i, 0);
             mbar_wait(&raw_full[rs], (i / S::NR) & 1);
             if (r == 0) wt_stamp(a.trace, team, i, 1);
@@ -320,9 +363,20 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
             }
         }
         if (r == 0) wt_stamp(a.trace, 3, WT_TRACE_IT - 1, 0);
-        const int m = mt * TC_M + r;
-        if (total > 0 && m < Mrows) {
-            const int t = m / g.Cin, ci = m - t * g.Cin;
+        int t, ci;
+        bool row_ok;
+        if (FLAT) {
+            const int kx = r / wg.G, cl = r - kx * wg.G;
+            row_ok = kx < g.KW && cl < f_ch;
+            t = f_ky * g.KW + kx;
+            ci = f_cg * wg.G + cl;
+        } else {
+            const int m = mt * TC_M + r;
+            row_ok = m < Mrows;
+            t = m / g.Cin;
+            ci = m - t * g.Cin;
+        }
+        if (total > 0 && row_ok) {
             if (!wg.swapped) {
                 // row = (tap, input channel), column = output channel:  Wbar[co][ci][t]
                 float* __restrict__ wrow = a.out + (long long)ci * KHW + t;
@@ -417,12 +471,12 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
     }
 }
 
-template <int BN>
+template <int BN, bool FLAT>
 static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, const WtGeom& wg) {
-    constexpr size_t smem = WtSmem<BN>::BYTES;
+    constexpr size_t smem = WtSmem<BN, FLAT>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("conv_wgrad_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
         attr_set = true;
     }
@@ -436,7 +490,7 @@ static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, 
         cudaMemset(d_tr, 0, n * sizeof(long long));
         ConvKArgs b = a;
         b.trace = d_tr;
-        conv_wgrad_tma_kernel<BN><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(b, maps, wg);
+        conv_wgrad_tma_kernel<BN, FLAT><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(b, maps, wg);
         cudaStreamSynchronize(st);
         std::vector<long long> h(n);
         cudaMemcpy(h.data(), d_tr, n * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -444,8 +498,8 @@ static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, 
         auto raw = [&](int role, int i, int slot) { return h[((size_t)role * WT_TRACE_IT + i) * 4 + slot]; };
         const long long t0 = raw(3, WT_TRACE_IT - 1, 2);
         auto at = [&](int role, int i, int slot) { const long long v = raw(role, i, slot); return v ? v - t0 : -1; };
-        fprintf(stderr, "WGT trace BN=%d Cin=%d Cout=%d k=%d W=%d grid=%d (clocks since kernel start); drain loop end %lld, epilogue end %lld\n", BN,
-                a.g.Cin, a.g.Cout, a.g.KH, a.g.W, wg.mtiles * wg.ntiles * wg.ksplit, at(3, WT_TRACE_IT - 1, 0), at(3, WT_TRACE_IT - 1, 1));
+        fprintf(stderr, "WGT trace BN=%d flat=%d Cin=%d Cout=%d k=%d W=%d grid=%d (clocks since kernel start); drain loop end %lld, epilogue end %lld\n", BN,
+                (int)FLAT, a.g.Cin, a.g.Cout, a.g.KH, a.g.W, wg.mtiles * wg.ntiles * wg.ksplit, at(3, WT_TRACE_IT - 1, 0), at(3, WT_TRACE_IT - 1, 1));
         for (int i = 0; i < WT_TRACE_IT - 1; ++i) {
             const int team = i & 1;
             if (at(2, i, 0) < 0) break;
@@ -455,32 +509,31 @@ static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, 
         }
         return 1;
     }
-    conv_wgrad_tma_kernel<BN><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(a, maps, wg);
+    conv_wgrad_tma_kernel<BN, FLAT><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(a, maps, wg);
     return 1;
 }
 
 // Returns 1 when the kernel was launched, 0 when the layer is not eligible, <0 on error.
 int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
-    static const int enabled = getenv("B2S_WGRAD_TMA") ? atoi(getenv("B2S_WGRAD_TMA")) : 1;
+    static const int enabled = getenv("B2S_WGRAD_TMA") ? atoi(getenv("B2S_WGRAD_TMA")) : 1;     // 0 = off, 1 = both forms, 2 = small maps only
     const int mode = get_tc_mode();
     if (!enabled || mode == 0) return 0;
     ConvKArgs a = a0;
     ConvGeom& g = a.g;
     const long long J = (long long)g.batch * g.OH * g.OW;
     if (g.sh != 1 || g.sw != 1 || g.H != g.OH || g.W != g.OW) return 0;
-    if (g.W != 8 && g.W != 16 && g.W != 32) return 0;
-    const int BH = TC_KB / g.W;
-    if (g.H % BH != 0 || J >= (1LL << 31)) return 0;
-    if (g.pw > 1 || g.KW - 1 - g.pw > 1) return 0;
+    if (g.pw > 1 || g.KW - 1 - g.pw > 1 || J >= (1LL << 31)) return 0;
     if ((g.in_sstride & 3) || (g.out_sstride & 3) || ((uintptr_t)a.out & 3)) return 0;
     for (int p = 0; p < a.npairs; ++p)
         if (((uintptr_t)a.act[p] & 15) || ((uintptr_t)a.wt[p] & 15)) return 0;
     if (mode == 1 && !tc_worth_it(J, g.Cin, g.Cout, g.KH * g.KW)) return 0;
     const int KHW = g.KH * g.KW;
+    const int BH = (g.W == 8 || g.W == 16 || g.W == 32) ? TC_KB / g.W : 0;
+    bool flat = !(BH > 0 && g.H % BH == 0);
     // which tensor is shifted (A rows = taps x its channels): for a "same" convolution the sum over output pixels of
     // g[co,px] x[ci,px+s] equals the sum over input pixels of x[ci,px'] g[co,px'-s] -- exchange the operands, mirror the
-    // taps.  k x k: the tensor with fewer channels (all its taps must fit one 128-row tile); 1x1: the one with MORE
-    // channels supplies the rows, the other one the (narrow) columns.
+    // taps.  k x k: the tensor with fewer channels; 1x1: the one with MORE channels supplies the rows, the other one the
+    // (narrower) columns.
     const bool same = 2 * g.ph == g.KH - 1 && 2 * g.pw == g.KW - 1;
     int swapped = 0;
     if (same && (KHW > 1 ? g.Cout < g.Cin : g.Cout > g.Cin)) {
@@ -489,47 +542,97 @@ int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
         std::swap(g.Cin, g.Cout);
         std::swap(g.in_sstride, g.out_sstride);
     }
-    if (KHW > 1 && KHW * g.Cin > TC_M) return 0;
+    if (!flat && KHW > 1 && KHW * g.Cin > TC_M) flat = true;           // the taps of the shifted tensor do not fit one tile
     const int BN = tc_choose_bn(g.Cout);
-    if (BN > 64) return 0;
+    if (!flat && BN > 64) flat = true;
+    if (flat && (enabled == 2 || (g.W & 3) || (KHW > 1 && !same))) return 0;
+    // a handful of shifted channels (VGG16 conv1_1: 3): a (vertical tap, channel group) tile would hold 9 of 128 rows --
+    // the gather kernel packs all 27 (tap, channel) rows into one tile (61 against 104 us)
+    if (flat && KHW > 1 && KHW * g.Cin <= 64) return 0;
     TmEncodeFn enc = tm_encoder();
     if (!enc) return 0;
-    WtGeom wg;
+    WtGeom wg{};
     wg.swapped = swapped;
-    wg.BH = BH;
-    wg.ndy = KHW == 1 ? 1 : g.KH;
-    wg.boxCa = KHW == 1 ? std::min(TC_M, (g.Cin + 7) & ~7) : g.Cin;
-    if ((long long)wg.ndy * wg.boxCa * 128 > (long long)WT_A_BYTES) return 0;
-    wg.mtiles = (KHW * g.Cin + TC_M - 1) / TC_M;
-    wg.ntiles = (g.Cout + BN - 1) / BN;
-    const int nkb = (int)(J / TC_KB);
-    static const int min_kb = getenv("B2S_WGT_MINKB") ? std::max(1, atoi(getenv("B2S_WGT_MINKB"))) : 16;
-    static const int max_ctas = getenv("B2S_WG_MAXCTAS") ? std::max(1, atoi(getenv("B2S_WG_MAXCTAS"))) : kNumSMs;
-    int ksplit = std::max(1, max_ctas / (wg.mtiles * wg.ntiles));
-    ksplit = std::min(ksplit, std::max(1, nkb / min_kb));
-    wg.ksplit = ksplit;
     WtMaps maps;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int p = 0; p < a.npairs; ++p) {
-        for (int which = 0; which < 2; ++which) {
-            const float* base = which == 0 ? a.act[p] : a.wt[p];
-            const int C = which == 0 ? g.Cin : g.Cout;
-            const long long ss = which == 0 ? g.in_sstride : g.out_sstride;
-            const cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)C, (cuuint64_t)g.batch};
-            const cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)ss * 4};
-            const cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)BH, (cuuint32_t)(which == 0 ? wg.boxCa : BN), 1};
-            const CUresult r = enc(which == 0 ? &maps.a[p] : &maps.b[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims,
-                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return 0;
+    int nkb;
+    if (!flat) {
+        wg.BH = BH;
+        wg.ndy = KHW == 1 ? 1 : g.KH;
+        wg.boxCa = KHW == 1 ? std::min(TC_M, (g.Cin + 7) & ~7) : g.Cin;
+        if ((long long)wg.ndy * wg.boxCa * 128 > (long long)WT_A_BYTES) return 0;
+        wg.mtiles = (KHW * g.Cin + TC_M - 1) / TC_M;
+        nkb = (int)(J / TC_KB);
+        for (int p = 0; p < a.npairs; ++p) {
+            for (int which = 0; which < 2; ++which) {
+                const float* base = which == 0 ? a.act[p] : a.wt[p];
+                const int C = which == 0 ? g.Cin : g.Cout;
+                const long long ss = which == 0 ? g.in_sstride : g.out_sstride;
+                const cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)C, (cuuint64_t)g.batch};
+                const cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)ss * 4};
+                const cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)BH, (cuuint32_t)(which == 0 ? wg.boxCa : BN), 1};
+                const CUresult r = enc(which == 0 ? &maps.a[p] : &maps.b[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims,
+                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return 0;
+            }
+        }
+    } else {
+        // m-tile = (vertical tap, channel group): its KW horizontal taps share ONE box of the group's channels
+        const int gmax = TC_M / g.KW;                                  // 42 channels for a 3 x 3 kernel, 128 for 1 x 1
+        wg.ncg = (g.Cin + gmax - 1) / gmax;
+        wg.G = (g.Cin + wg.ncg - 1) / wg.ncg;
+        wg.mtiles = g.KH * wg.ncg;
+        wg.kpi = (g.H * g.W + TC_KB - 1) / TC_KB;
+        nkb = g.batch * wg.kpi;
+        const long long HW = (long long)g.H * g.W;
+        for (int p = 0; p < a.npairs; ++p) {
+            for (int which = 0; which < 2; ++which) {
+                const float* base = which == 0 ? a.act[p] : a.wt[p];
+                const int C = which == 0 ? g.Cin : g.Cout;
+                const long long ss = which == 0 ? g.in_sstride : g.out_sstride;
+                const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)g.batch};
+                const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)ss * 4};
+                const cuuint32_t box[3] = {(cuuint32_t)(which == 0 ? WT_FLAT_ROW : TC_KB), (cuuint32_t)(which == 0 ? wg.G : BN), 1};
+                const CUresult r = enc(which == 0 ? &maps.a[p] : &maps.b[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims,
+                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return 0;
+            }
         }
     }
+    wg.ntiles = (g.Cout + BN - 1) / BN;
+    static const int min_kb = getenv("B2S_WGT_MINKB") ? std::max(1, atoi(getenv("B2S_WGT_MINKB"))) : 16;
+    static const int max_ctas = getenv("B2S_WG_MAXCTAS") ? std::max(1, atoi(getenv("B2S_WG_MAXCTAS"))) : kNumSMs;
+    // split-K: the number of slices that minimises (waves of CTAs) x (k-blocks per CTA + ~4 k-blocks' worth of prologue and
+    // epilogue), at least min_kb k-blocks per slice -- 156 tiles (VGG16 conv4_x) would otherwise run as one full wave plus
+    // a second wave of 8 CTAs
+    const int tiles = wg.mtiles * wg.ntiles;
+    const int ks_max = std::max(1, nkb / min_kb);
+    int ksplit = 1;
+    double best = 1e30;
+    for (int ks = 1; ks <= ks_max && ks <= 4 * max_ctas; ++ks) {
+        const int waves = (tiles * ks + max_ctas - 1) / max_ctas;
+        const double cost = waves * ((double)((nkb + ks - 1) / ks) + 4.0);
+        if (cost < best - 1e-9) { best = cost; ksplit = ks; }
+    }
+    wg.ksplit = ksplit;
     for (int p = a.npairs; p < kMaxPairs; ++p) { maps.a[p] = maps.a[0]; maps.b[p] = maps.b[0]; }
+    if (flat) {
+        switch (BN) {
+        case 16: return launch_wt_t<16, true>(st, a, maps, wg);
+        case 32: return launch_wt_t<32, true>(st, a, maps, wg);
+        case 48: return launch_wt_t<48, true>(st, a, maps, wg);
+        case 64: return launch_wt_t<64, true>(st, a, maps, wg);
+        case 96: return launch_wt_t<96, true>(st, a, maps, wg);
+        default: return launch_wt_t<128, true>(st, a, maps, wg);
+        }
+    }
     switch (BN) {
-    case 16: return launch_wt_t<16>(st, a, maps, wg);
-    case 32: return launch_wt_t<32>(st, a, maps, wg);
-    case 48: return launch_wt_t<48>(st, a, maps, wg);
-    default: return launch_wt_t<64>(st, a, maps, wg);
+    case 16: return launch_wt_t<16, false>(st, a, maps, wg);
+    case 32: return launch_wt_t<32, false>(st, a, maps, wg);
+    case 48: return launch_wt_t<48, false>(st, a, maps, wg);
+    default: return launch_wt_t<64, false>(st, a, maps, wg);
     }
 }
 

@@ -1160,6 +1160,11 @@ int b2s_profile_pass(b2s_plan* p, int32_t order, int32_t reps, b2s_prof_entry* o
     if (order < 3) B2S_TRY(alloc_order(p, order));
     Profiler prof;
     int rc = 0;
+    // every kernel is timed ALONE: the weight-gradient leaves run on the main stream while profiling (on their side
+    // streams the event pair of a leaf would also measure its wait for SMs behind the main chain's kernels -- round 2's
+    // bench line carried 39 us per weight-gradient launch for a kernel that takes 17-26 us)
+    const bool side = p->wgrad_side;
+    p->wgrad_side = false;
     rc = run_pass_eager(p, order);                   // warm-up, untimed
     if (rc == 0) {
         g_prof = &prof;
@@ -1167,6 +1172,7 @@ int b2s_profile_pass(b2s_plan* p, int32_t order, int32_t reps, b2s_prof_entry* o
         g_prof = nullptr;
     }
     cudaStreamSynchronize(p->stream);
+    p->wgrad_side = side;
     std::map<std::string, b2s_prof_entry> agg;
     std::vector<std::string> order_seen;
     const size_t per_pass = prof.recs.size() / (size_t)reps;

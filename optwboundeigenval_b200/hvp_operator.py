@@ -386,7 +386,11 @@ class B200HVPOperator(object):
         _require_cuda()
         _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.model = model.to(self.device)
+        # opt.py:56 moves the model; when every parameter and buffer already lives on the device that is a no-op which
+        # still walks all modules (1.8 ms per minibatch for DenseNet3, on the critical path of the regularised step)
+        if any(t.device != self.device for t in model.parameters()) or any(t.device != self.device for t in model.buffers()):
+            model = model.to(self.device)
+        self.model = model
         self.data = data
         self.criterion = criterion
         self.use_gpu = True
@@ -409,9 +413,9 @@ class B200HVPOperator(object):
     def zero_grad(self, model=None):
         if model is None:
             model = self.model
-        for p in model.parameters():
-            if p.grad is not None:
-                p.grad.data.zero_()
+        grads = [p.grad for p in model.parameters() if p.grad is not None]
+        if grads:                                     # one multi-tensor launch instead of one kernel per parameter
+            torch._foreach_zero_(grads)
 
     def prep_data(self, data):
         if type(data) == list or type(data) == tuple:
