@@ -52,16 +52,26 @@ constexpr uint32_t WT_A_BYTES = TC_M * 128;    // 128 rows x 32 pixels of fp32: 
 //               a ragged last k-block of an image is zero-filled as well); the horizontal taps read the box at +-1 pixel
 //               and mask the pixels whose neighbour lies in the next image row.
 constexpr int WT_FLAT_ROW = 40;                // floats per raw row of the shifted tensor in FLAT mode (4 + 32 + 4)
-template <int BN, bool FLAT>
+// TS = true (small maps, W in {16, 32}): the 128-row operand goes through TMEM (tcgen05.mma with A in TMEM, as conv_tma.cu)
+//   instead of shared-memory hi / lo images: one thread per row reads the row's 32 pixels from the raw box -- which TMA
+//   lands with a 128-byte (W = 32) or 64-byte (W = 16) swizzle, so that the 8 lanes of a quarter warp hit 8 (4) different
+//   bank groups although their rows are 128 bytes apart --, shifts them in registers (the neighbours outside the k-block's
+//   row are padding), splits and stores hi / lo with tcgen05.st.  Only the narrow operand keeps swizzled hi / lo images
+//   in shared memory.  Per k-block the shared-memory traffic drops from 126 KB to ~68 KB (BN = 48).
+template <int BN, bool FLAT, bool TS>
 struct WtSmem {
     static constexpr int NST = BN >= 96 ? 2 : 3;                              // operand stages
-    static constexpr int NR = FLAT ? 2 : (BN <= 48 ? 4 : 3);                  // raw stages
+    // raw stages: the TS form consumes a k-block in ~600 clocks, so a box (~1600 clocks from request to landing) has to be
+    // requested more than three k-blocks ahead -- with four stages the timeline showed the teams waiting for TMA
+    static constexpr int NR = FLAT ? 2 : TS ? (BN <= 48 ? 8 : 6) : (BN <= 48 ? 4 : 3);
     static constexpr uint32_t B_BYTES = BN * 128;
-    static constexpr uint32_t STAGE_BYTES = 2 * WT_A_BYTES + 2 * B_BYTES;     // A hi | A lo | B hi | B lo
+    static constexpr uint32_t B_OFF = TS ? 0u : 2 * WT_A_BYTES;               // B hi image inside a stage
+    static constexpr uint32_t STAGE_BYTES = B_OFF + 2 * B_BYTES;              // [A hi | A lo |] B hi | B lo
     static constexpr uint32_t RAW_A_BYTES = FLAT ? TC_M * WT_FLAT_ROW * 4 : WT_A_BYTES;
     static constexpr uint32_t RAW_BYTES = RAW_A_BYTES + B_BYTES;              // raw A boxes | raw B box
     static constexpr size_t BYTES = (size_t)NST * STAGE_BYTES + (size_t)NR * RAW_BYTES + 256 + 1024;
     static_assert(BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(!(TS && FLAT) && !(TS && BN > 64), "TS form: small maps only");
 };
 
 struct alignas(64) WtMaps {
@@ -74,6 +84,7 @@ struct WtGeom {
     int BH;                                    // image rows per k-block: W * BH = 32
     int ndy;                                   // vertical taps = boxes of the shifted tensor per k-block (1 for a 1x1 kernel)
     int boxCa;                                 // channels per box of the shifted tensor
+    int a_box_al;                              // bytes between the boxes of consecutive vertical taps (1024-byte aligned)
     // FLAT mode: an m-tile = (vertical tap ky, channel group of G channels), rows = kx * G + channel
     int G, ncg;                                // channels per group, groups
     int kpi;                                   // k-blocks per image = ceil(H * W / 32)
@@ -119,11 +130,11 @@ __device__ __forceinline__ void wt_split_store(uint8_t* hi_img, uint8_t* lo_img,
     *reinterpret_cast<float4*>(lo_img + off) = lo;
 }
 
-template <int BN, bool FLAT>
+template <int BN, bool FLAT, bool TS>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, const WtGeom wg) {
     extern __shared__ uint8_t wt_smem_raw[];
-    using S = WtSmem<BN, FLAT>;
+    using S = WtSmem<BN, FLAT, TS>;
     constexpr int WT_NST = S::NST;
     uint8_t* smem = wt_smem_raw + ((1024u - (smem_u32(wt_smem_raw) & 1023u)) & 1023u);      // swizzle atoms: 1024-byte aligned
     uint8_t* stages = smem;
@@ -180,11 +191,11 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
             const int y0 = (j0 - n * HW) / W;
             mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)wg.ndy * a_box + b_box);
             for (int d = 0; d < wg.ndy; ++d)
-                tma_load_4d(dst + (size_t)d * a_box, &maps.a[p], 0, one ? y0 : y0 + d - g.ph, one ? mt * TC_M : 0, n, &raw_full[rs]);
+                tma_load_4d(dst + (size_t)d * wg.a_box_al, &maps.a[p], 0, one ? y0 : y0 + d - g.ph, one ? mt * TC_M : 0, n, &raw_full[rs]);
             tma_load_4d(dst + S::RAW_A_BYTES, &maps.b[p], 0, y0, nt * BN, n, &raw_full[rs]);
         }
     };
-    const int prefill = min(S::NR, total);
+    const int prefill = min(S::NR < 4 ? S::NR : 4, total);        // the rest of a deeper ring is requested behind the barrier (32 TMA issues before it delayed every role by ~3000 clocks)
     if (warp == WT_WARP_TMA && lane == 0) {
         for (int s = 0; s < S::NR; ++s) {
             mbar_init(&raw_full[s], 1);
@@ -225,13 +236,13 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
                 else {
                     const int t = m / g.Cin, ca = m - t * g.Cin;
                     const int ky = t / g.KW, kx = t - ky * g.KW;
-                    e = ((ky * wg.boxCa + ca) * 32) * 4 + (kx - g.pw + 1);
+                    e = (ky * (wg.a_box_al >> 2) + ca * 32) * 4 + (kx - g.pw + 1);
                 }
             }
         }
         row_tab[tid] = e;
     }
-    if (rows_here < TC_M) {   // A rows past the last valid one are never written: zero the stages once
+    if (!TS && rows_here < TC_M) {   // A rows past the last valid one are never written: zero the stages once
         float4* z = reinterpret_cast<float4*>(stages);
         const int n4 = WT_NST * (int)S::STAGE_BYTES / 16;
         for (int i = tid; i < n4; i += WT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -242,7 +253,85 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
+    if (TS && warp < 8) {
+        // ===================== transform, TS form: thread = row of the 128-row operand -> TMEM; narrow operand -> smem =====
+        const int team = warp >> 2;
+        const int r = tid & 127;
+        const int kg = r & 7, rowsub = r >> 3;                  // narrow operand: 4-pixel group kg of rows rowsub + 16 u
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int e = row_tab[r];
+        const bool row_ok = e >= 0;
+        const int adx = row_ok ? (e & 3) - 1 : 0;
+        const uint32_t row_off = row_ok ? (uint32_t)(e >> 2) * 4u : 0u;           // byte offset of this row inside the raw A area
+        // physical 16-byte chunk of logical chunk j: TMA's swizzle XORs the chunk index with the 128-byte row index
+        const uint32_t swz = W == 32 ? ((row_off >> 7) & 7u) : ((row_off >> 7) & 3u);
+        const bool warp_ok = __any_sync(0xffffffffu, row_ok);
+        uint32_t doff[BN / 16];
+#pragma unroll
+        for (int u = 0; u < BN / 16; ++u) {
+            const int rl = rowsub + 16 * u;
+            doff[u] = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((kg ^ (rl & 7)) << 4));
+        }
+        constexpr int NB = BN / 16;
+        for (int i = team; i < total; i += 2) {
+            const int rs = i % S::NR;
+            const int s = i % WT_NST;
+            const uint32_t round = i / WT_NST;
+            const uint8_t* rawA = raws + (size_t)rs * S::RAW_BYTES;
+            const float* __restrict__ rawB = reinterpret_cast<const float*>(rawA + S::RAW_A_BYTES);
+            if (r == 0) wt_stamp(a.trace, team, i, 0);
+            mbar_wait(&raw_full[rs], (i / S::NR) & 1);
+            if (r == 0) wt_stamp(a.trace, team, i, 1);
+            float v[34];                                        // v[1 + k] = pixel k of this row; v[0], v[33]: outside the k-block = padding
+            v[0] = 0.f; v[33] = 0.f;
+            if (warp_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t ph = W == 32 ? (((uint32_t)j ^ swz) << 4) : ((uint32_t)(j >> 2) * 64u + ((((uint32_t)j & 3u) ^ swz) << 4));
+                    const float4 c4 = row_ok ? *reinterpret_cast<const float4*>(rawA + row_off + ph) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[1 + 4 * j] = c4.x; v[2 + 4 * j] = c4.y; v[3 + 4 * j] = c4.z; v[4 + 4 * j] = c4.w;
+                }
+            }
+            float4 cb[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) cb[u] = *reinterpret_cast<const float4*>(rawB + (rowsub + 16 * u) * 32 + kg * 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_free[rs]);          // the boxes are in registers: the producer may refill the stage
+            if (round > 0) mbar_wait(&ab_free[s], (round - 1) & 1);
+            __syncwarp();
+            tc_fence_after();
+            if (r == 0) wt_stamp(a.trace, team, i, 2);
+            if (warp_ok) {
+                const uint32_t col = (uint32_t)(s * TC_ACOLS);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int t8 = 0; t8 < 8; ++t8) {
+                        const int k = j8 * 8 + t8;
+                        // horizontal tap: the neighbour inside the image row, zero across a row end (W = 16: two rows per k-block)
+                        float f = v[1 + k];
+                        if (adx < 0) f = (W == 16 && k == 16) ? 0.f : v[k];
+                        else if (adx > 0) f = (W == 16 && k == 15) ? 0.f : v[2 + k];
+                        hi[t8] = (__float_as_uint(f) + 0x1000u) & 0xffffe000u;
+                        lo[t8] = __float_as_uint(f - __uint_as_float(hi[t8]));
+                    }
+                    tmem_st8(lane_addr + col + j8 * 8, hi);
+                    tmem_st8(lane_addr + col + 32 + j8 * 8, lo);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            uint8_t* Bhi = stages + (size_t)s * S::STAGE_BYTES + S::B_OFF;
+            uint8_t* Blo = Bhi + S::B_BYTES;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) wt_split_store(Bhi, Blo, doff[u], cb[u]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the tensor core
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ab_full[s]);
+            if (r == 0) wt_stamp(a.trace, team, i, 3);
+        }
+    } else if (warp < 8) {
         // ===================== transform: raw boxes -> registers (shift, split) -> swizzled operand stage =========
         const int team = warp >> 2;
         const int r = tid & 127;
@@ -306,7 +395,7 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
             if (r == 0) wt_stamp(a.trace, team, i, 2);
             uint8_t* Ahi = stages + (size_t)s * S::STAGE_BYTES;
             uint8_t* Alo = Ahi + WT_A_BYTES;
-            uint8_t* Bhi = Alo + WT_A_BYTES;
+            uint8_t* Bhi = Ahi + S::B_OFF;
             uint8_t* Blo = Bhi + S::B_BYTES;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -424,14 +513,27 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
                 if (lane == 0) wt_stamp(a.trace, 2, i, 2);
                 const uint32_t d_addr = tmem_u + TC_DCOL0 + b * TC_DCOLS;
                 const uint64_t dAh = desc0 + (uint64_t)(s * STAGE16), dAl = dAh + A16;
-                const uint64_t dBh = dAl + A16, dBl = dBh + B16;
+                const uint64_t dBh = desc0 + (uint64_t)(s * STAGE16) + (uint64_t)(S::B_OFF >> 4), dBl = dBh + B16;
+                const uint32_t a_hi = tmem_u + (uint32_t)(s * TC_ACOLS), a_lo = a_hi + 32;      // TS form: A stage in TMEM
                 const uint32_t cont = first ? 0u : 1u;
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < TC_KB / 8; ++ks) {
                         const uint64_t ko = (uint64_t)(ks * 2);           // 32 bytes per k-step inside the 128-byte swizzle row
                         const uint32_t accf = ks >= 1 ? 1u : cont;
-                        if (NACC == 3) {
+                        if (TS) {
+                            if (NACC == 3) {
+                                umma_tf32_ts(d_addr + BN, a_hi + ks * 8, dBh + ko, idesc2, accf);     // [hi*hi | hi*lo]
+                                umma_tf32_ts(d_addr, a_lo + ks * 8, dBh + ko, idesc, accf);           // lo*hi
+                            } else if (NACC == 2) {
+                                umma_tf32_ts(d_addr, a_hi + ks * 8, dBh + ko, idesc2, accf);
+                                umma_tf32_ts(d_addr + BN, a_lo + ks * 8, dBh + ko, idesc, 1u);
+                            } else {
+                                umma_tf32_ts(d_addr, a_hi + ks * 8, dBl + ko, idesc, accf);
+                                umma_tf32_ts(d_addr, a_lo + ks * 8, dBh + ko, idesc, 1u);
+                                umma_tf32_ts(d_addr, a_hi + ks * 8, dBh + ko, idesc, 1u);
+                            }
+                        } else if (NACC == 3) {
                             umma_tf32_ss(d_addr + BN, dAh + ko, dBh + ko, idesc2, accf);      // [hi*hi | hi*lo]
                             umma_tf32_ss(d_addr, dAl + ko, dBh + ko, idesc, accf);            // lo*hi
                         } else if (NACC == 2) {
@@ -454,7 +556,7 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
             // ===================== producer: the boxes of a k-block, NR k-blocks ahead ===============
             for (int i = prefill; i < total; ++i) {
                 if (lane == 0) {
-                    mbar_wait(&raw_free[i % S::NR], ((uint32_t)(i / S::NR) - 1) & 1);
+                    if (i >= S::NR) mbar_wait(&raw_free[i % S::NR], ((uint32_t)(i / S::NR) - 1) & 1);
                     request(i);
                 }
                 __syncwarp();
@@ -471,18 +573,19 @@ conv_wgrad_tma_kernel(const ConvKArgs a, const __grid_constant__ WtMaps maps, co
     }
 }
 
-template <int BN, bool FLAT>
+template <int BN, bool FLAT, bool TS>
 static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, const WtGeom& wg) {
-    constexpr size_t smem = WtSmem<BN, FLAT>::BYTES;
+    constexpr size_t smem = WtSmem<BN, FLAT, TS>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, FLAT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("conv_wgrad_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
         attr_set = true;
     }
     static const bool want_trace = getenv("B2S_WG_TRACE") != nullptr;
     static int traced = 0;
-    if (want_trace && traced < 6 && a.g.KH == (getenv("B2S_WG_TRACE_K") ? atoi(getenv("B2S_WG_TRACE_K")) : 3)) {   // debug: synchronous launch + timeline of CTA 0
+    if (want_trace && traced < 6 && a.g.KH == (getenv("B2S_WG_TRACE_K") ? atoi(getenv("B2S_WG_TRACE_K")) : 3) &&
+        (!getenv("B2S_WG_TRACE_W") || a.g.W == atoi(getenv("B2S_WG_TRACE_W")))) {   // debug: synchronous launch + timeline of CTA 0
         ++traced;
         long long* d_tr = nullptr;
         const size_t n = 4 * WT_TRACE_IT * 4;
@@ -490,7 +593,7 @@ static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, 
         cudaMemset(d_tr, 0, n * sizeof(long long));
         ConvKArgs b = a;
         b.trace = d_tr;
-        conv_wgrad_tma_kernel<BN, FLAT><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(b, maps, wg);
+        conv_wgrad_tma_kernel<BN, FLAT, TS><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(b, maps, wg);
         cudaStreamSynchronize(st);
         std::vector<long long> h(n);
         cudaMemcpy(h.data(), d_tr, n * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -498,8 +601,8 @@ static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, 
         auto raw = [&](int role, int i, int slot) { return h[((size_t)role * WT_TRACE_IT + i) * 4 + slot]; };
         const long long t0 = raw(3, WT_TRACE_IT - 1, 2);
         auto at = [&](int role, int i, int slot) { const long long v = raw(role, i, slot); return v ? v - t0 : -1; };
-        fprintf(stderr, "WGT trace BN=%d flat=%d Cin=%d Cout=%d k=%d W=%d grid=%d (clocks since kernel start); drain loop end %lld, epilogue end %lld\n", BN,
-                (int)FLAT, a.g.Cin, a.g.Cout, a.g.KH, a.g.W, wg.mtiles * wg.ntiles * wg.ksplit, at(3, WT_TRACE_IT - 1, 0), at(3, WT_TRACE_IT - 1, 1));
+        fprintf(stderr, "WGT trace BN=%d flat=%d ts=%d Cin=%d Cout=%d k=%d W=%d grid=%d (clocks since kernel start); drain loop end %lld, epilogue end %lld\n", BN,
+                (int)FLAT, (int)TS, a.g.Cin, a.g.Cout, a.g.KH, a.g.W, wg.mtiles * wg.ntiles * wg.ksplit, at(3, WT_TRACE_IT - 1, 0), at(3, WT_TRACE_IT - 1, 1));
         for (int i = 0; i < WT_TRACE_IT - 1; ++i) {
             const int team = i & 1;
             if (at(2, i, 0) < 0) break;
@@ -509,7 +612,7 @@ static int launch_wt_t(cudaStream_t st, const ConvKArgs& a, const WtMaps& maps, 
         }
         return 1;
     }
-    conv_wgrad_tma_kernel<BN, FLAT><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(a, maps, wg);
+    conv_wgrad_tma_kernel<BN, FLAT, TS><<<wg.mtiles * wg.ntiles * wg.ksplit, WT_THREADS, smem, st>>>(a, maps, wg);
     return 1;
 }
 
@@ -553,6 +656,8 @@ int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
     if (!enc) return 0;
     WtGeom wg{};
     wg.swapped = swapped;
+    static const int ts_on = getenv("B2S_WGRAD_TS") ? atoi(getenv("B2S_WGRAD_TS")) : 1;
+    const bool ts = ts_on && !flat && (g.W == 32 || g.W == 16) && BN <= 64;
     WtMaps maps;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     int nkb;
@@ -560,7 +665,8 @@ int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
         wg.BH = BH;
         wg.ndy = KHW == 1 ? 1 : g.KH;
         wg.boxCa = KHW == 1 ? std::min(TC_M, (g.Cin + 7) & ~7) : g.Cin;
-        if ((long long)wg.ndy * wg.boxCa * 128 > (long long)WT_A_BYTES) return 0;
+        wg.a_box_al = (wg.boxCa * 128 + 1023) & ~1023;
+        if ((long long)wg.ndy * wg.a_box_al > (long long)WT_A_BYTES) return 0;
         wg.mtiles = (KHW * g.Cin + TC_M - 1) / TC_M;
         nkb = (int)(J / TC_KB);
         for (int p = 0; p < a.npairs; ++p) {
@@ -571,8 +677,11 @@ int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
                 const cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)C, (cuuint64_t)g.batch};
                 const cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)ss * 4};
                 const cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)BH, (cuuint32_t)(which == 0 ? wg.boxCa : BN), 1};
+                // TS form: the 128-row operand's box is landed swizzled so that one thread per row reads it without bank conflicts
+                const CUtensorMapSwizzle swz = (ts && which == 0) ? (g.W == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)
+                                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
                 const CUresult r = enc(which == 0 ? &maps.a[p] : &maps.b[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims,
-                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) return 0;
             }
@@ -620,19 +729,27 @@ int try_launch_wgrad_tma(cudaStream_t st, const ConvKArgs& a0) {
     for (int p = a.npairs; p < kMaxPairs; ++p) { maps.a[p] = maps.a[0]; maps.b[p] = maps.b[0]; }
     if (flat) {
         switch (BN) {
-        case 16: return launch_wt_t<16, true>(st, a, maps, wg);
-        case 32: return launch_wt_t<32, true>(st, a, maps, wg);
-        case 48: return launch_wt_t<48, true>(st, a, maps, wg);
-        case 64: return launch_wt_t<64, true>(st, a, maps, wg);
-        case 96: return launch_wt_t<96, true>(st, a, maps, wg);
-        default: return launch_wt_t<128, true>(st, a, maps, wg);
+        case 16: return launch_wt_t<16, true, false>(st, a, maps, wg);
+        case 32: return launch_wt_t<32, true, false>(st, a, maps, wg);
+        case 48: return launch_wt_t<48, true, false>(st, a, maps, wg);
+        case 64: return launch_wt_t<64, true, false>(st, a, maps, wg);
+        case 96: return launch_wt_t<96, true, false>(st, a, maps, wg);
+        default: return launch_wt_t<128, true, false>(st, a, maps, wg);
+        }
+    }
+    if (ts) {
+        switch (BN) {
+        case 16: return launch_wt_t<16, false, true>(st, a, maps, wg);
+        case 32: return launch_wt_t<32, false, true>(st, a, maps, wg);
+        case 48: return launch_wt_t<48, false, true>(st, a, maps, wg);
+        default: return launch_wt_t<64, false, true>(st, a, maps, wg);
         }
     }
     switch (BN) {
-    case 16: return launch_wt_t<16, false>(st, a, maps, wg);
-    case 32: return launch_wt_t<32, false>(st, a, maps, wg);
-    case 48: return launch_wt_t<48, false>(st, a, maps, wg);
-    default: return launch_wt_t<64, false>(st, a, maps, wg);
+    case 16: return launch_wt_t<16, false, false>(st, a, maps, wg);
+    case 32: return launch_wt_t<32, false, false>(st, a, maps, wg);
+    case 48: return launch_wt_t<48, false, false>(st, a, maps, wg);
+    default: return launch_wt_t<64, false, false>(st, a, maps, wg);
     }
 }
 
