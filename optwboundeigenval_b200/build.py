@@ -28,6 +28,8 @@ if os.environ.get("B2S_BUILD_TRUNC"):          # experiment: truncating TF32 spl
     CFLAGS.append("-DB2S_TMA_TRUNC")
 if os.environ.get("B2S_BUILD_TM_G"):           # experiment: k-blocks per drain group in conv_tma.cu
     CFLAGS.append("-DB2S_TM_G=" + os.environ["B2S_BUILD_TM_G"])
+if os.environ.get("B2S_BUILD_TM_TEAMS"):       # experiment: three transform teams for narrow tiles in conv_tma.cu
+    CFLAGS.append("-DB2S_TM_TEAMS=" + os.environ["B2S_BUILD_TM_TEAMS"])
 if os.environ.get("B2S_BUILD_TRACE"):          # per-role clock stamps in the tcgen05 kernel (tools/tc_trace.py)
     CFLAGS.append("-DB2S_TC_TRACE_ENABLED")
 

@@ -38,11 +38,21 @@
 
 namespace b2s {
 
-constexpr int TM_THREADS = 512;
-constexpr int TM_XFORM_THREADS = 256;
-constexpr int TM_WARP_MMA = 12;
-constexpr int TM_WARP_B = 13;
-constexpr int TM_WARP_RAW = 14;
+// Transform teams of 128 threads.  The per-role timeline of the TS-form weight gradient (conv_wgrad_tma.cu) suggested that the
+// split -> tcgen05.st -> wait::st -> fence -> arrive phase (~1000 clocks per team and k-block, one warp per scheduler working
+// through ~260 dependent instructions) paces this kernel: two teams give one k-block per ~455 clocks.  Experiment
+// (B2S_BUILD_TM_TEAMS=3): narrow tiles (BN <= 48) with THREE teams -- 640 threads at 96 registers, each team owning one of
+// the three A stages.  Measured: DenseNet3 HVP 2.273 -> 2.262 ms, i.e. nothing -- the k-loop is not paced by the transform
+// alone -- so the default stays at two teams.  What the experiment did teach: setmaxnreg.inc can only take what
+// setmaxnreg.dec of the SAME CTA has released (the pool is the CTA's launch allocation, not the SM's register file): with
+// 640 threads at 96 registers the four misc warps release 4 x 32 x (96 - 40), so the drain warps can go to 152 at most;
+// asking for 168 blocked forever.
+#ifndef B2S_TM_TEAMS
+#define B2S_TM_TEAMS 2
+#endif
+__host__ __device__ constexpr int tm_teams(int BN) { return (B2S_TM_TEAMS == 3 && BN <= 48) ? 3 : 2; }
+__host__ __device__ constexpr int tm_threads(int BN) { return (tm_teams(BN) * 4 + 8) * 32; }
+__host__ __device__ constexpr int tm_regs_drain(int BN) { return tm_teams(BN) == 3 ? 152 : TC_REGS_DRAIN; }
 constexpr int TM_NR = 4;                               // raw activation stages (TMA boxes of <= 16 KB)
 constexpr int TM_RAW_FLOATS = TC_M * TC_KB;            // floats reserved per raw stage
 #ifndef B2S_TM_G
@@ -85,7 +95,7 @@ __device__ __forceinline__ void tm_stamp(long long* trace, int role, uint32_t kb
 }
 
 template <int BN, int MODE, int PT>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+__global__ void __launch_bounds__(tm_threads(BN), 1)
 conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const TmaTiling tg) {
     extern __shared__ __align__(1024) uint8_t tm_smem[];
     pdl_trigger();                                            // the next kernel may be scheduled behind this one
@@ -120,6 +130,10 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
     const int dbg = tg.dbg;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = tm_teams(BN);                           // transform teams
+    constexpr int TM_XFORM_THREADS = NT * 128;
+    constexpr int TM_WARP_DRAIN0 = NT * 4;                     // first drain warp
+    constexpr int TM_WARP_MMA = NT * 4 + 4, TM_WARP_B = NT * 4 + 5, TM_WARP_RAW = NT * 4 + 6;
 
     if (tid == 0) {
         for (int s = 0; s < TM_NR; ++s) {
@@ -148,7 +162,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                                               // everything above overlapped the previous kernel's tail
 
-    if (warp < 8) {
+    if (warp < TM_WARP_DRAIN0) {
         // ===================== transform: landed box -> registers (shift, split) -> TMEM =====================
         // PT = pixels of one image inside the tile (128, or the image size when the tile holds several images)
         const int r = tid & 127, team = tid >> 7, q = warp & 3;
@@ -168,7 +182,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                         if (tid == 0) tm_stamp(a.trace, 3, kbg, 3);
                         const float* __restrict__ raw = rawbuf + rs * TM_RAW_FLOATS + roff;
                         for (int kx = 0; kx < g.KW; ++kx, ++kbg) {
-                            if ((int)(kbg & 1) != team) continue;
+                            if ((int)(kbg % NT) != team) continue;
                             if ((tid & 127) == 0) tm_stamp(a.trace, 0, kbg, 0);
                             const int dx = MODE == MODE_FWD ? kx - g.pw : g.pw - kx;
                             const bool ok = (unsigned)(x + dx) < (unsigned)W;
@@ -220,10 +234,10 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                 }
             }
         }
-    } else if (warp < 12) {
+    } else if (warp < TM_WARP_DRAIN0 + 4) {
         // ===================== drain + epilogue: TMEM -> fp32 registers -> NCHW global ===============
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_DRAIN));
-        const int q = warp - 8;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tm_regs_drain(BN)));
+        const int q = warp - TM_WARP_DRAIN0;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t grp = 0;                                       // drain groups of TM_G k-blocks (never across pairs)
@@ -237,11 +251,11 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                 const float sc = a.scale[p];
                 for (int k0 = 0; k0 < KBp; k0 += TM_G, ++grp) {
                     const int b = grp & 1;
-                    if (tid == 256) tm_stamp(a.trace, 2, grp, 0);
+                    if (tid == TM_XFORM_THREADS) tm_stamp(a.trace, 2, grp, 0);
                     tm_wait(&d_full[b], (grp >> 1) & 1, dbg, 300 + b);
                     __syncwarp();
                     tc_fence_after();
-                    if (tid == 256) tm_stamp(a.trace, 2, grp, 1);
+                    if (tid == TM_XFORM_THREADS) tm_stamp(a.trace, 2, grp, 1);
                     // with 6 accumulators the odd-k-step set is only written by k-blocks of >= 2 k-steps
                     // (k-block order (ky, chunk, kx): the chunk index is (kbl / KW) % nchunks)
                     bool odd_set = false;
@@ -278,7 +292,7 @@ conv_tma_kernel(const ConvKArgs a, const __grid_constant__ TmaMaps maps, const T
                     }
                     tc_fence_before();
                     mbar_arrive(&d_empty[b]);
-                    if (tid == 256) tm_stamp(a.trace, 2, grp, 2);
+                    if (tid == TM_XFORM_THREADS) tm_stamp(a.trace, 2, grp, 2);
                 }
             }
             // epilogue: lane = pixel, so every per-channel store is one coalesced 128-byte row.  The variant
@@ -466,7 +480,7 @@ static int launch_tma_t(cudaStream_t st, const ConvKArgs& a, const TmaMaps& maps
         cudaMemset(d_tr, 0, n * sizeof(long long));
         ConvKArgs b = a;
         b.trace = d_tr;
-        conv_tma_kernel<BN, MODE, PT><<<grid, TM_THREADS, smem, st>>>(b, maps, tg);
+        conv_tma_kernel<BN, MODE, PT><<<grid, tm_threads(BN), smem, st>>>(b, maps, tg);
         cudaStreamSynchronize(st);
         std::vector<long long> h(n);
         cudaMemcpy(h.data(), d_tr, n * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -484,7 +498,7 @@ static int launch_tma_t(cudaStream_t st, const ConvKArgs& a, const TmaMaps& maps
         return 1;
     }
     {
-        const cudaError_t e = launch_pdl(conv_tma_kernel<BN, MODE, PT>, dim3(grid), dim3(TM_THREADS), smem, st, a, maps, tg);
+        const cudaError_t e = launch_pdl(conv_tma_kernel<BN, MODE, PT>, dim3(grid), dim3(tm_threads(BN)), smem, st, a, maps, tg);
         if (e != cudaSuccess) { set_error("conv_tma launch: %s", cudaGetErrorString(e)); return -3; }
     }
     if (tg.dbg & 7) {
