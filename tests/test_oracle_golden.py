@@ -76,3 +76,34 @@ def test_bn_running_stats_side_effect():
     op.gradient()
     flat = np.concatenate([v.detach().reshape(-1).double().numpy() for v in model.state_dict().values()])
     assert rel_err(flat, g["state_after_one_pass"]) < 1e-6
+
+
+def test_closed_form_rop_specification():
+    """rop.py (the reference's written R-operator specification: sigmoid MLP, 0.5*||yhat - y||^2, one sample) run
+    unmodified by oracle/make_rop_golden.py: dE/dw, R{dE/dw} = Hv and R^2{dE/dw} = vGHv (rop.py:103-164) must be what
+    the autograd oracle computes for the same network, weights and direction (fp64, biases carry no direction)."""
+    g = load_golden("rop_sigmoid_mlp")
+    n, L = int(g["n"]), int(g["layers"])
+    layers = []
+    for i in range(L):
+        lin = torch.nn.Linear(n, n).double()
+        lin.weight.data = torch.from_numpy(g["w%d" % i]).clone()
+        lin.bias.data = torch.from_numpy(g["b%d" % i][:, 0]).clone()
+        layers += [lin, torch.nn.Sigmoid()]
+    model = torch.nn.Sequential(*layers)
+    x = torch.from_numpy(g["x"].T.copy())
+    y = torch.from_numpy(g["y"].T.copy())
+    op = ao.AutogradSpectralOperator(model, [x, y], lambda out, tgt: 0.5 * ((out - tgt) ** 2).sum())
+    # direction: rop.py:81 reshapes slice i column-major into the [out, in] matrix of layer i; nn.Linear is row-major
+    parts = []
+    for i in range(L):
+        parts += [np.reshape(g["v"][i * n * n:(i + 1) * n * n, 0], (n, n), order="F").reshape(-1), np.zeros(n)]
+    v = torch.from_numpy(np.concatenate(parts))
+    grad, hv, vghv = op.gradient().detach().numpy(), op.hv(v).numpy(), op.vghv(v).numpy()
+    off = 0
+    for i in range(L):
+        sl = slice(off, off + n * n)
+        assert rel_err(grad[sl], g["g%d" % i].reshape(-1)) < 1e-12
+        assert rel_err(hv[sl], g["hv%d" % i].reshape(-1)) < 1e-12
+        assert rel_err(vghv[sl], g["vghv%d" % i].reshape(-1)) < 1e-11
+        off += n * n + n
