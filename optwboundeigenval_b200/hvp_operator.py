@@ -128,7 +128,8 @@ class SpectralPlan:
     def _head_inputs(self, target, batch, gbatch, use_global):
         head = self.tape.head
         if head in (HEAD_CE, HEAD_SOFTMAX_CE):
-            return target.to(self.device, torch.int64).contiguous().view(-1), None, 1.0 / float(gbatch)
+            nc = self.tape.tensors[self.tape.logits].numel
+            return target.to(self.device, torch.int64).contiguous().view(-1), None, self.tape.head_scale(gbatch, nc)
         t = target.to(self.device, torch.float32)
         if t.dim() == 1:
             t = t.view(-1, 1)
@@ -153,7 +154,9 @@ class SpectralPlan:
         _lib.check(self.lib.b2s_eval_pass(self.handle, _ptr(params), _ptr(x), _ptr(y), _ptr(coef), batch, scale,
                                           _ptr(logits), _ptr(loss)), "b2s_eval_pass")
         self._keep = (params, x, y, coef)
-        if self.tape.head == HEAD_SOFTMAX_CE:
+        if self.tape.kl_reduction is not None:
+            logits = torch.log_softmax(logits, dim=1)
+        elif self.tape.head == HEAD_SOFTMAX_CE:
             logits = torch.softmax(logits, dim=1)
         elif self.tape.head == HEAD_SIGMOID_WBCE:
             logits = torch.sigmoid(logits)
@@ -297,7 +300,7 @@ def plan_for(model, criterion, x: torch.Tensor, device, max_batch=None) -> Spect
     if device.type == "cuda" and device.index is None:        # the reference says torch.device('cuda') (opt.py:247)
         device = torch.device("cuda", torch.cuda.current_device())
     shape = tuple(x.shape[1:])
-    key = (id(model), criterion.__class__.__name__, shape)
+    key = (id(model), criterion.__class__.__name__, getattr(criterion, "reduction", None), shape)
     entry = _PLANS.get(key)
     batch = int(x.shape[0])
     if entry is not None:

@@ -98,6 +98,16 @@ class Tape:
     bn_modules: List[nn.Module] = field(default_factory=list)
     param_offsets: Dict[int, int] = field(default_factory=dict)
     conv_layers: List[int] = field(default_factory=list)     # op indices of Conv/Linear, first use per module
+    # KLDivLoss on a one-hot target (opt.py:182-185,566-569): cross entropy of the logits times this reduction factor
+    kl_reduction: Optional[str] = None
+
+    def head_scale(self, batch: int, classes: int) -> float:
+        """factor on the SUM over samples of the per-sample cross entropy"""
+        if self.kl_reduction is None or self.kl_reduction == "batchmean":
+            return 1.0 / float(batch)
+        if self.kl_reduction == "mean":                       # nn.KLDivLoss default: mean over all B*C elements
+            return 1.0 / (float(batch) * float(classes))
+        return 1.0                                            # "sum"
 
     def c_tensors(self):
         arr = (CTensor * len(self.tensors))()
@@ -132,6 +142,8 @@ def _pair(v):
 
 def head_kind(criterion, tail: Optional[str]) -> int:
     name = criterion.__class__.__name__
+    if tail == "log_softmax" and name != "KLDivLoss":
+        raise UnsupportedModel("log_softmax output is supported with KLDivLoss only")
     if name == "CrossEntropyLoss":
         if getattr(criterion, "reduction", "mean") != "mean" or getattr(criterion, "weight", None) is not None \
                 or getattr(criterion, "label_smoothing", 0.0) != 0.0 or getattr(criterion, "ignore_index", -100) != -100:
@@ -143,7 +155,17 @@ def head_kind(criterion, tail: Optional[str]) -> int:
         if tail == "softmax":
             raise UnsupportedModel("softmax output followed by the weighted BCE loss is not supported")
         return HEAD_SIGMOID_WBCE if tail == "sigmoid" else HEAD_WBCE
-    raise UnsupportedModel("loss %s has no B200 head (supported: CrossEntropyLoss, W_BCEWithLogitsLoss)" % name)
+    if name == "KLDivLoss":
+        # opt.py:182-185: criterion(output, one_hot(target)).  With log-probabilities as the model output (what
+        # KLDivLoss takes) and a one-hot target, sum_c t*(log t - out) = -log_softmax(z)[y]: the cross-entropy head on
+        # the logits, scaled by the loss's reduction (Tape.head_scale).
+        if tail != "log_softmax":
+            raise UnsupportedModel("KLDivLoss needs a model that ends in log_softmax (it takes log-probabilities)")
+        if getattr(criterion, "log_target", False) or getattr(criterion, "reduction", "mean") not in ("mean", "batchmean", "sum"):
+            raise UnsupportedModel("KLDivLoss is supported with log_target=False and reduction mean / batchmean / sum")
+        return HEAD_CE
+    raise UnsupportedModel("loss %s has no B200 head (supported: CrossEntropyLoss, W_BCEWithLogitsLoss, KLDivLoss on "
+                           "log-probabilities)" % name)
 
 
 class _Builder:
@@ -322,7 +344,7 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
                 raise UnsupportedModel("the model must return a single tensor")
             continue
         if tail is not None:
-            raise UnsupportedModel("%s: softmax / sigmoid is supported only as the last op of the model" % nm)
+            raise UnsupportedModel("%s: softmax / log_softmax / sigmoid is supported only as the last op of the model" % nm)
 
         def arg(i, key=None, default=None):
             if len(node.args) > i:
@@ -378,6 +400,11 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
             elif isinstance(m, nn.Sigmoid):
                 env[node] = t
                 tail = "sigmoid"
+            elif isinstance(m, nn.LogSoftmax):
+                if m.dim not in (1, -1):
+                    raise UnsupportedModel("%s: log_softmax over dim %r" % (nm, m.dim))
+                env[node] = t
+                tail = "log_softmax"
             else:
                 raise UnsupportedModel("module %s (%s) has no B200 kernel" % (node.target, m.__class__.__name__))
         elif node.op == "call_function":
@@ -417,6 +444,11 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
             elif _is_fn(tg, torch.sigmoid, F.sigmoid):
                 env[node] = tin(node.args[0])
                 tail = "sigmoid"
+            elif _is_fn(tg, F.log_softmax, torch.log_softmax):
+                if arg(1, "dim", None) not in (1, -1):
+                    raise UnsupportedModel("%s: log_softmax over dim %r" % (nm, arg(1, "dim", None)))
+                env[node] = tin(node.args[0])
+                tail = "log_softmax"
             elif _is_fn(tg, F.dropout):
                 if arg(1, "p", 0.5) > 0 and arg(2, "training", True):
                     raise UnsupportedModel("%s: dropout with p > 0" % nm)
@@ -462,7 +494,10 @@ def trace(model: nn.Module, criterion, input_shape) -> Tape:
     if result is None:
         raise UnsupportedModel("model returns nothing")
     head = head_kind(criterion, tail)
-    return _finish(b, result, head, input_shape)
+    tape = _finish(b, result, head, input_shape)
+    if tail == "log_softmax":
+        tape.kl_reduction = getattr(criterion, "reduction", "mean")
+    return tape
 
 
 def _unsupported(nm, why):

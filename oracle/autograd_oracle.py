@@ -61,7 +61,12 @@ class AutogradSpectralOperator:
         """opt.py:175-192 (prepare_grad): forward, loss, grad with graph, flatten, cast to fp64."""
         if self._g is None:
             out = self.model(self.inputs)
-            loss = self.criterion(out, self.target)
+            if self.criterion.__class__.__name__ == "KLDivLoss":       # opt.py:182-185: one-hot target
+                onehot = torch.zeros(out.shape)
+                onehot.scatter_(1, self.target.view(-1, 1), 1)
+                loss = self.criterion(out.float(), onehot.float())
+            else:
+                loss = self.criterion(out, self.target)
             self.loss_value = float(loss.detach())
             g = torch.autograd.grad(loss, self.params(), create_graph=True)
             self._g = _flatten(g).double()

@@ -298,3 +298,29 @@ def test_dnet_custom_function_modules_lower_to_relu_and_linear():
     assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 1e-10
     assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 1e-9
     assert rel_err(jo.vghv(v).numpy(), op.vghv(v).numpy()) < 1e-8
+
+
+@pytest.mark.parametrize("reduction", ["mean", "batchmean", "sum"])
+def test_kldiv_one_hot_branch_is_the_cross_entropy_head(reduction):
+    """opt.py:182-185: KLDivLoss(model(x), one_hot(y)).  On log-probabilities that is the cross entropy of the logits
+    times the reduction factor, which is how the tracer lowers it (Tape.head_scale); fp32 as the reference casts."""
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(9, 12), torch.nn.ReLU(), torch.nn.Linear(12, 5),
+                                torch.nn.LogSoftmax(dim=1))
+    loss = torch.nn.KLDivLoss(reduction=reduction)
+    x, y = torch.randn(6, 9), torch.randint(0, 5, (6,))
+    tape = tracer.trace(model, loss, (9,))
+    assert tape.head == tracer.HEAD_CE and tape.kl_reduction == reduction
+    op = ao.AutogradSpectralOperator(model, [x, y], loss)
+    P = tape.n_params
+    v = torch.randn(P, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    jo = JetTapeOracle(tape, ao.flat_params(model).double(), x, y, loss_scale=tape.head_scale(6, 5))
+    assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 2e-6
+    assert abs(float(jo.loss) - op.loss_value) < 1e-6 * abs(op.loss_value)
+    assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 2e-5
+    assert rel_err(jo.vghv(v).numpy(), op.vghv(v).numpy()) < 2e-4
+    with pytest.raises(tracer.UnsupportedModel):
+        tracer.trace(model[:3], loss, (9,))                  # raw logits into KLDivLoss
+    with pytest.raises(tracer.UnsupportedModel):
+        tracer.trace(model, torch.nn.CrossEntropyLoss(), (9,))
