@@ -519,16 +519,31 @@ def run_b200(args):
         cur.synchronize()
         np.multiply(rh, 1.0 / np.sqrt(np.dot(rh, rh)), out=vh)          # next input depends on this output
 
-    for _ in range(warmup):
-        e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    # The host-side normalisation between two calls is 176 k doubles: a threaded BLAS parks its workers during the
+    # 2.3 ms the host waits for the device and pays their wake-up on every np.dot (measured: p95 of 20 ms against a
+    # median of 40 us, the 212 .. 394 HVP/s spread of this figure between boxes), so the dot runs on the calling thread.
+    try:
+        from threadpoolctl import threadpool_limits
+        blas_one = threadpool_limits(limits=1, user_api="blas")
+    except Exception:                                   # threadpoolctl missing: keep numpy's default
+        blas_one = None
+    e2e_ms = []
+    try:
+        for _ in range(warmup):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            t_step = time.perf_counter()
+            e2e_step()
+            e2e_ms.append(1e3 * (time.perf_counter() - t_step))
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+    finally:
+        if blas_one is not None:
+            blas_one.restore_original_limits()
 
     # ---- second headline metric: regularised steps/sec ---------------------------------------------
     # one step = the minibatch body of iter() (opt.py:608-699): host batch -> device, new operator, base pass,
@@ -683,7 +698,9 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": _config(kind, batch, world),
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * P},
+                        "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * P,
+                        "host_step_ms_median": float(np.median(e2e_ms)), "host_step_ms_max": float(np.max(e2e_ms)),
+                        "vs_device_resident": ms / ms_e2e},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": roof,
