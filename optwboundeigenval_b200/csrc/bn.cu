@@ -611,6 +611,300 @@ __global__ void __launch_bounds__(1024) bn_bwd_chanc_kernel(const BnArgs a, floa
     }
 }
 
+// ---- a CLUSTER of R CTAs per channel, each with its share of the channel cached in shared memory ------------------
+// The cached one-CTA form stops where a channel's operands exceed one SM's shared memory: DenseNet3's first dense block
+// (32 x 32 maps, batch 32: 393 KB forward, 655 KB adjoint at order 1) fell back to the cooperative kernels -- two trips
+// to memory and a GRID barrier per layer (14 / 19.5 us per launch against 7 / 10.6 us of the cached form on the
+// four-times-smaller block-2 maps).  Here R = 2, 4 or 8 CTAs of one thread-block cluster share a channel: CTA r caches
+// chunks [r n, (r+1) n) of the channel, pushes its two partial sums into slot r of EVERY cluster member's shared
+// memory (distributed shared memory), and after ONE cluster barrier every CTA adds the R partials of its own copy in
+// rank order (bitwise the same total everywhere).  Nobody touches remote shared memory after that barrier, so CTAs may
+// exit independently.  The first barrier phase (arrive at kernel entry, wait before the remote stores) is the
+// "all CTAs of the cluster have started" guarantee distributed shared memory needs.  Single GPU only.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// thread 0 of every CTA: partial (v[0], v[1]) -> total over the cluster in tot[]; all threads must call
+__device__ __forceinline__ void cluster_total2(double (*part)[2], const double* v, double* tot, unsigned r, unsigned R) {
+    cg::cluster_group cluster = cg::this_cluster();
+    if (threadIdx.x == 0) {
+        for (unsigned t = 0; t < R; ++t) {
+            double* dst = cluster.map_shared_rank(&part[0][0], t);
+            dst[2 * r + 0] = v[0];
+            dst[2 * r + 1] = v[1];
+        }
+    }
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (unsigned t = 0; t < R; ++t) { t0 += part[t][0]; t1 += part[t][1]; }
+        tot[0] = t0; tot[1] = t1;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(1024) bn_fwd_clus_kernel(const BnArgs a, int do_stats, int R) {
+    extern __shared__ float4 bn_cache[];
+    __shared__ double red[64];
+    __shared__ double part[8][2];
+    __shared__ BnChanRaw sch;
+    cluster_arrive();                                  // phase 1: "this CTA runs"
+    const unsigned r = cg::this_cluster().block_rank();
+    const int c = blockIdx.x / R;
+    const unsigned Q = (unsigned)(a.HW / 4);
+    const unsigned n = (unsigned)a.batch * Q / (unsigned)R;       // chunks cached by this CTA
+    const unsigned base = r * n;
+    const long long coff = (long long)c * a.HW;
+    const bool mask = a.relu && K > 0;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned gi = base + i, s = gi / Q, q = gi - s * Q;
+        const long long off = coff + (long long)q * 4;
+        const long long ii = (long long)s * a.in_sstride + off, oi = (long long)s * a.out_sstride + off;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) bn_cache[k * n + i] = a.x[k] ? ld4(a.x[k], ii) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mask) bn_cache[(K + 1) * n + i] = ld4(a.y0, oi);
+    }
+    double tot[2] = {0.0, 0.0};
+    double v[2] = {0.0, 0.0};
+    if (do_stats) {
+        const double N = (double)a.count;
+        float mu0 = 0.f, mu1 = 0.f;
+        if (K >= 1) mu0 = (float)(a.fsum[0][0 * a.C + c] / N);
+        if (K >= 2) mu1 = (float)(a.fsum[1][0 * a.C + c] / N);
+        double T = 0, Qs = 0;
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+            const float4 v0 = bn_cache[i];
+            float4 v1 = v0, v2 = v0;
+            if (K >= 1) v1 = bn_cache[n + i];
+            if (K >= 2) v2 = bn_cache[2 * n + i];
+            float t = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x0 = f4(v0, e);
+                if (K == 0) {
+                    t += x0;
+                    Qs += (double)x0 * x0;
+                } else if (K == 1) {
+                    const float x1 = f4(v1, e);
+                    t += x1;
+                    Qs += 2.0 * (double)((x0 - mu0) * x1);
+                } else {
+                    const float x1 = f4(v1, e), x2 = f4(v2, e);
+                    const float c1 = x1 - mu1;
+                    t += x2;
+                    Qs += 2.0 * (double)(c1 * c1 + (x0 - mu0) * x2);
+                }
+            }
+            T += (double)t;
+        }
+        v[0] = T; v[1] = Qs;
+        block_sum<2, double>(v, red);
+    }
+    cluster_wait();                                    // phase 1 complete: every CTA of the cluster has started
+    if (do_stats) {
+        cluster_total2(part, v, tot, r, (unsigned)R);
+        if (threadIdx.x == 0 && r == 0) {              // single writer per channel (later passes read the sums)
+            a.fsum[K][0 * a.C + c] = tot[0];
+            a.fsum[K][1 * a.C + c] = tot[1];
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double* ovr = do_stats ? tot : nullptr;
+        to_raw<K>(bn_channel<K>(a, c, ovr), sch);
+        if (K == 0 && r == 0 && a.running_mean) {
+            const double N = (double)a.count;
+            const double mu = (ovr ? ovr[0] : a.fsum[0][0 * a.C + c]) / N;
+            double var = (ovr ? ovr[1] : a.fsum[0][1 * a.C + c]) / N - mu * mu;
+            if (var < 0) var = 0;
+            const double unb = N > 1 ? var * N / (N - 1) : var;
+            const double m = (double)a.momentum;
+            a.running_mean[c] = (float)((1.0 - m) * (double)a.running_mean[c] + m * mu);
+            a.running_var[c] = (float)((1.0 - m) * (double)a.running_var[c] + m * unb);
+        }
+    }
+    __syncthreads();
+    const BnChan<K> ch = from_raw<K>(sch);
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned gi = base + i, s = gi / Q, q = gi - s * Q;
+        const long long oi = (long long)s * a.out_sstride + coff + (long long)q * 4;
+        const float4 v0 = bn_cache[i];
+        float4 v1 = v0, v2 = v0, m0 = v0;
+        if (K >= 1) v1 = bn_cache[n + i];
+        if (K >= 2) v2 = bn_cache[2 * n + i];
+        if (mask) m0 = bn_cache[(K + 1) * n + i];
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const Jet<K, float> xj(f4(v0, e), K >= 1 ? f4(v1, e) : 0.f, K >= 2 ? f4(v2, e) : 0.f);
+            const Jet<K, float> xh = (xj - ch.mu) * ch.r;
+            const Jet<K, float> y = ch.gam * xh + ch.bet;
+            float rr = y.c[K];
+            if (a.relu) {
+                if (K == 0) rr = rr > 0.f ? rr : 0.f;
+                else rr = f4(m0, e) > 0.f ? rr : 0.f;
+            }
+            o[e] = rr;
+        }
+        *reinterpret_cast<float4*>(a.yk + oi) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(1024) bn_bwd_clus_kernel(const BnArgs a, float pgrad_scale, int R) {
+    extern __shared__ float4 bn_cache[];
+    __shared__ double red[64];
+    __shared__ double part[8][2];
+    __shared__ BnChanRaw sch;
+    __shared__ float sm[2][3];
+    cluster_arrive();                                  // phase 1: "this CTA runs"
+    const unsigned r = cg::this_cluster().block_rank();
+    const int c = blockIdx.x / R;
+    const unsigned Q = (unsigned)(a.HW / 4);
+    const unsigned n = (unsigned)a.batch * Q / (unsigned)R;
+    const unsigned base = r * n;
+    const long long coff = (long long)c * a.HW;
+    constexpr int SY = K + 1, SG = K + 2;          // slots: x_0..x_K | y0 | g_0..g_K
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned gi = base + i, s = gi / Q, q = gi - s * Q;
+        const long long off = coff + (long long)q * 4;
+        const long long ii = (long long)s * a.in_sstride + off, oi = (long long)s * a.out_sstride + off;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+            bn_cache[k * n + i] = a.x[k] ? ld4(a.x[k], ii) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bn_cache[(SG + k) * n + i] = a.g[k] ? ld4(a.g[k], oi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (a.relu) bn_cache[SY * n + i] = ld4(a.y0, oi);
+    }
+    if (threadIdx.x == 0) to_raw<K>(bn_channel<K>(a, c), sch);      // forward sums of all orders are final
+    __syncthreads();
+    const BnChan<K> ch = from_raw<K>(sch);
+    double G = 0, X = 0;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        float4 xv[3], gv[3], m0 = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int k = 0; k <= K; ++k) { xv[k] = bn_cache[k * n + i]; gv[k] = bn_cache[(SG + k) * n + i]; }
+        if (a.relu) m0 = bn_cache[SY * n + i];
+        float gs = 0.f, xs = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (a.relu && !(f4(m0, e) > 0.f)) continue;
+            const Jet<K, float> xj(f4(xv[0], e), K >= 1 ? f4(xv[1], e) : 0.f, K >= 2 ? f4(xv[2], e) : 0.f);
+            const Jet<K, float> ge(f4(gv[0], e), K >= 1 ? f4(gv[1], e) : 0.f, K >= 2 ? f4(gv[2], e) : 0.f);
+            const Jet<K, float> xh = (xj - ch.mu) * ch.r;
+            gs += ge.c[K];
+            xs += (ge * xh).c[K];
+        }
+        G += (double)gs;
+        X += (double)xs;
+    }
+    double v[2] = {G, X};
+    block_sum<2, double>(v, red);
+    cluster_wait();                                    // phase 1 complete: every CTA of the cluster has started
+    double tot[2] = {0.0, 0.0};
+    cluster_total2(part, v, tot, r, (unsigned)R);
+    if (threadIdx.x == 0) {
+        if (r == 0) {
+            a.bsum[K][0 * a.C + c] = tot[0];
+            a.bsum[K][1 * a.C + c] = tot[1];
+        }
+        const double N = (double)a.count;
+        Jet<K, float> Gj, Xj;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+            Gj.c[k] = (float)((k == K ? tot[0] : a.bsum[k][0 * a.C + c]) / N);
+            Xj.c[k] = (float)((k == K ? tot[1] : a.bsum[k][1 * a.C + c]) / N);
+        }
+        const Jet<K, float> t1 = ch.gam * Gj, t2 = ch.gam * Xj;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sm[0][k] = t1.c[k]; sm[1][k] = t2.c[k]; }
+        if (r == 0) {
+            atomicAdd(a.out_beta + c, (float)(tot[0] * (double)pgrad_scale));
+            atomicAdd(a.out_gamma + c, (float)(tot[1] * (double)pgrad_scale));
+        }
+    }
+    __syncthreads();
+    if (a.xbar == nullptr) return;
+    Jet<K, float> m1, m2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m1.c[k] = sm[0][k]; m2.c[k] = sm[1][k]; }
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned gi = base + i, s = gi / Q, q = gi - s * Q;
+        const long long ii = (long long)s * a.in_sstride + coff + (long long)q * 4;
+        float4 xv[3], gv[3], m0 = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int k = 0; k <= K; ++k) { xv[k] = bn_cache[k * n + i]; gv[k] = bn_cache[(SG + k) * n + i]; }
+        if (a.relu) m0 = bn_cache[SY * n + i];
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.accumulate) prev = ld4(a.xbar, ii);
+        float o[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const Jet<K, float> xj(f4(xv[0], e), K >= 1 ? f4(xv[1], e) : 0.f, K >= 2 ? f4(xv[2], e) : 0.f);
+            const Jet<K, float> xh = (xj - ch.mu) * ch.r;
+            Jet<K, float> ge;
+            if (!a.relu || f4(m0, e) > 0.f) ge = Jet<K, float>(f4(gv[0], e), K >= 1 ? f4(gv[1], e) : 0.f, K >= 2 ? f4(gv[2], e) : 0.f);
+            const Jet<K, float> u = ch.gam * ge - m1 - xh * m2;
+            const Jet<K, float> xb = ch.r * u;
+            o[e] += xb.c[K];
+        }
+        *reinterpret_cast<float4*>(a.xbar + ii) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// cluster size of the clustered cached form, or 0 when it does not apply or is not asked for: single GPU,
+// 128-bit path, the channel too large for one CTA's cache but small enough for eight
+static inline int bn_cluster_size(const BnArgs& a, int vec, int order, bool bwd, size_t* smem) {
+    // Measured on DenseNet3 at batch 32 (13 block-1 layers, every kernel timed alone): forward 0.502 -> 0.477 ms, adjoint
+    // 0.624 -> 0.673 ms (655 KB per channel: 384 .. 768 CTAs of 82 KB need two to three waves of 296 slots), the HVP
+    // step unchanged at 2.31 ms -- the grid barrier was not what paces these layers.  Hence opt-in (B2S_BN_CLUSTER=1);
+    // read per launch (launches are captured once per plan) so that the parity test can toggle it.
+    const char* sw = getenv("B2S_BN_CLUSTER");
+    if (!sw || atoi(sw) == 0 || vec != 4 || a.C < 8 || a.peer) return 0;
+    const size_t n = (size_t)a.batch * a.HW / 4;
+    const int slots = bwd ? 2 * (order + 1) + 1 : (order + 1) + 1;
+    const size_t bytes = n * slots * sizeof(float4);
+    int R = 0;
+    for (int r = 2; r <= 8; r *= 2)
+        if (n % r == 0 && bytes / r <= 100 * 1024) { R = r; break; }       // two CTAs per SM
+    if (!R && n % 8 == 0 && bytes / 8 <= 200 * 1024) R = 8;                // one CTA per SM
+    if (!R) return 0;
+    while (R < 8 && (long long)a.C * R < kNumSMs && n % (2 * R) == 0 && n / (2 * R) >= 1024) R *= 2;
+    *smem = bytes / R;
+    return R;
+}
+template <int K>
+static int launch_clus(cudaStream_t st, const BnArgs& a, bool bwd, size_t smem, int R, int do_stats) {
+    static bool attr_f = false, attr_b = false;
+    if (!bwd && !attr_f) {
+        B2S_CUDA(cudaFuncSetAttribute(bn_fwd_clus_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_f = true;
+    }
+    if (bwd && !attr_b) {
+        B2S_CUDA(cudaFuncSetAttribute(bn_bwd_clus_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_b = true;
+    }
+    const size_t n = (size_t)a.batch * a.HW / 4 / R;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.C * R)); cfg.blockDim = dim3(smem > 100 * 1024 ? 1024 : n >= 1024 ? 512 : 256);     // <= 100 KB: two CTAs per SM (36 .. 63 registers)
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (bwd) e = cudaLaunchKernelEx(&cfg, bn_bwd_clus_kernel<K>, a, a.pgrad_scale, R);
+    else e = cudaLaunchKernelEx(&cfg, bn_fwd_clus_kernel<K>, a, do_stats, R);
+    if (e != cudaSuccess) { set_error("clustered BN launch: %s", cudaGetErrorString(e)); return -3; }
+    count_launch();
+    return 0;
+}
+static int launch_clus_order(cudaStream_t st, int order, const BnArgs& a, bool bwd, size_t smem, int R, int do_stats) {
+    return order == 0 ? launch_clus<0>(st, a, bwd, smem, R, do_stats) : order == 1 ? launch_clus<1>(st, a, bwd, smem, R, do_stats)
+                                                                                  : launch_clus<2>(st, a, bwd, smem, R, do_stats);
+}
+
 // shared-memory bytes of the cached form, or 0 when it does not apply (128-bit path only; B2S_BN_CACHED=0 switches it off)
 static inline size_t bn_cached_smem(const BnArgs& a, int vec, int order, bool bwd) {
     static const int on = getenv("B2S_BN_CACHED") ? atoi(getenv("B2S_BN_CACHED")) : 1;
@@ -720,6 +1014,10 @@ int launch_bn_fwd_fused(cudaStream_t st, int order, const BnArgs& a, int do_stat
     if (skip_family("bn_fwd")) return 0;
     const int vec = bn_vec(a);
     if (const size_t smem = bn_cached_smem(a, vec, order, false)) return launch_chanc_order(st, order, a, false, smem, do_stats);
+    {
+        size_t csm = 0;
+        if (const int R = bn_cluster_size(a, vec, order, false, &csm)) return launch_clus_order(st, order, a, false, csm, R, do_stats);
+    }
     if (const int blk = bn_chan_block(a, vec)) {
         BnArgs b = a;
         if (b.peer_ll == 2) { b.peer = nullptr; b.peer_ll = 0; }     // single GPU: one block per channel needs no barrier at all
@@ -740,6 +1038,10 @@ int launch_bn_bwd_fused(cudaStream_t st, int order, const BnArgs& a) {
     if (skip_family("bn_bwd")) return 0;
     const int vec = bn_vec(a);
     if (const size_t smem = bn_cached_smem(a, vec, order, true)) return launch_chanc_order(st, order, a, true, smem, 1);
+    {
+        size_t csm = 0;
+        if (const int R = bn_cluster_size(a, vec, order, true, &csm)) return launch_clus_order(st, order, a, true, csm, R, 1);
+    }
     if (const int blk = bn_chan_block(a, vec)) {
         const float ps = a.pgrad_scale;
         BnArgs b = a;
