@@ -208,13 +208,21 @@ class _Builder:
     # ---- layer lowering ------------------------------------------------------------------
     def conv(self, t, m: nn.Conv2d, name):
         c, h, w = self.vts[t].shape
-        if m.groups != 1 or _pair(m.dilation) != (1, 1) or m.padding_mode != "zeros" or isinstance(m.padding, str):
+        if m.groups != 1 or _pair(m.dilation) != (1, 1) or m.padding_mode != "zeros":
             raise UnsupportedModel("%s: grouped / dilated / non-zero-padded convolutions are not supported" % name)
         if c != m.in_channels:
             raise UnsupportedModel("%s: expected %d input channels, got %d" % (name, m.in_channels, c))
         kh, kw = _pair(m.kernel_size)
         sh, sw = _pair(m.stride)
-        ph, pw = _pair(m.padding)
+        if isinstance(m.padding, str):                       # torch's spellings of the two symmetric cases
+            if m.padding == "valid":
+                ph = pw = 0
+            elif m.padding == "same" and kh % 2 == 1 and kw % 2 == 1 and (sh, sw) == (1, 1):
+                ph, pw = kh // 2, kw // 2
+            else:
+                raise UnsupportedModel("%s: padding=%r needs asymmetric padding" % (name, m.padding))
+        else:
+            ph, pw = _pair(m.padding)
         oh = (h + 2 * ph - kh) // sh + 1
         ow = (w + 2 * pw - kw) // sw + 1
         return self.add_op(OP_CONV, t, (m.out_channels, oh, ow), w_off=self.poff[id(m.weight)],

@@ -324,3 +324,135 @@ def test_kldiv_one_hot_branch_is_the_cross_entropy_head(reduction):
         tracer.trace(model[:3], loss, (9,))                  # raw logits into KLDivLoss
     with pytest.raises(tracer.UnsupportedModel):
         tracer.trace(model, torch.nn.CrossEntropyLoss(), (9,))
+
+
+class _RandomNet(torch.nn.Module):
+    """A seeded small network mixing everything the tracer lowers: biased / unbiased convolutions of odd geometry,
+    BatchNorm with and without ReLU, both poolings, DenseNet-style concatenation, a residual add, a parameter shared
+    by two call sites, a softmax tail."""
+
+    def __init__(self, rng):
+        super().__init__()
+        nn = torch.nn
+        pick = lambda *a: a[int(rng.integers(len(a)))]                      # noqa: E731
+        self.c0 = int(pick(3, 5))
+        c1, c2 = int(pick(6, 8)), int(pick(4, 7))
+        self.k1, self.s1 = int(pick(1, 3, 5)), int(pick(1, 2))
+        self.conv1 = nn.Conv2d(self.c0, c1, self.k1, stride=self.s1, padding=self.k1 // 2, bias=bool(pick(0, 1)))
+        self.bn1 = nn.BatchNorm2d(c1)
+        self.conv2 = nn.Conv2d(c1, c2, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(c1 + c2)
+        self.conv3 = nn.Conv2d(c1 + c2, c1 + c2, int(pick(1, 3)), padding="same", bias=bool(pick(0, 1)))
+        self.pool = nn.MaxPool2d(2) if pick(0, 1) else nn.AvgPool2d(2)
+        self.shared = nn.Linear(c1 + c2, c1 + c2)
+        self.fc = nn.Linear(c1 + c2, 4)
+        self.tail = bool(pick(0, 1))
+
+    def forward(self, x):
+        F = torch.nn.functional
+        h = F.relu(self.bn1(self.conv1(x)))
+        h = torch.cat([h, self.conv2(h)], 1)                 # DenseNet-style growth
+        h = self.bn2(h)                                       # BatchNorm without ReLU
+        h = F.relu(h + self.conv3(h))                         # residual add
+        h = self.pool(h)
+        h = torch.flatten(F.adaptive_avg_pool2d(h, (1, 1)), 1)
+        h = F.relu(self.shared(h))
+        h = F.relu(self.shared(h))                            # same Linear twice (forest_data.py:75-89)
+        h = self.fc(h)
+        return F.softmax(h, dim=1) if self.tail else h
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_architectures_jets_match_autograd_fp64(seed):
+    rng = np.random.default_rng(100 + seed)
+    torch.manual_seed(200 + seed)
+    model = _RandomNet(rng).train()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    hw = int(rng.choice([8, 12]))
+    g = torch.Generator().manual_seed(300 + seed)
+    batch = int(rng.choice([3, 5]))
+    x = torch.randn(batch, model.c0, hw, hw, generator=g)
+    y = torch.randint(0, 4, (batch,), generator=g)
+    loss = torch.nn.CrossEntropyLoss()
+    tape = tracer.trace(model, loss, (model.c0, hw, hw))
+    model64 = model.double()
+    op = ao.AutogradSpectralOperator(model64, [x.double(), y], loss)
+    P = tape.n_params
+    assert P == sum(p.numel() for p in model.parameters())
+    v = torch.randn(P, generator=g, dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    jo = JetTapeOracle(tape, ao.flat_params(model64), x, y)
+    assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 1e-10
+    assert abs(float(jo.loss) - op.loss_value) < 1e-10
+    assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 1e-9
+    assert rel_err(jo.vghv(v, mode="reference").numpy(), op.vghv(v).numpy()) < 1e-8
+
+
+def _head(c):
+    nn = torch.nn
+    return [nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten(), nn.Linear(c, 4)]
+
+
+def _edge_models():
+    nn = torch.nn
+    conv = lambda *a, **k: nn.Conv2d(*a, **k)                                                   # noqa: E731
+    ok = {
+        "maxpool 3 s2 p1 (DenseNet121 stem)": (nn.Sequential(conv(3, 6, 3, padding=1), nn.ReLU(), nn.MaxPool2d(3, 2, 1), *_head(6)), (3, 9, 9)),
+        "maxpool 3 s2 (AlexNet)": (nn.Sequential(conv(3, 6, 3, padding=1), nn.ReLU(), nn.MaxPool2d(3, 2), *_head(6)), (3, 9, 9)),
+        "maxpool 2 p1 (VGG transit, dcnn.py:238-252)": (nn.Sequential(conv(3, 6, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2, padding=1), *_head(6)), (3, 8, 8)),
+        "avgpool 2 on an odd map": (nn.Sequential(conv(3, 6, 3, padding=1), nn.ReLU(), nn.AvgPool2d(2), *_head(6)), (3, 9, 9)),
+        "conv 5 s2 p2 + BN + in-place ReLU": (nn.Sequential(conv(3, 6, 5, 2, 2), nn.BatchNorm2d(6), nn.ReLU(inplace=True), *_head(6)), (3, 9, 9)),
+        "rectangular kernel": (nn.Sequential(conv(3, 6, (3, 1), padding=(1, 0)), nn.ReLU(), *_head(6)), (3, 8, 8)),
+        "rectangular input": (nn.Sequential(conv(3, 6, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(), nn.Linear(90, 4)), (3, 6, 10)),
+        "padding='same' / 'valid'": (nn.Sequential(conv(3, 6, 3, padding="same"), nn.ReLU(), conv(6, 6, 3, padding="valid"), *_head(6)), (3, 8, 8)),
+        "BatchNorm on the input": (nn.Sequential(nn.BatchNorm2d(3), conv(3, 6, 3, padding=1), nn.ReLU(), *_head(6)), (3, 8, 8)),
+        "ReLU on the input, ReLU twice": (nn.Sequential(nn.ReLU(), conv(3, 6, 3, padding=1), nn.ReLU(), nn.ReLU(), *_head(6)), (3, 8, 8)),
+        "BatchNorm1d after Linear": (nn.Sequential(nn.Flatten(), nn.Linear(12, 8), nn.BatchNorm1d(8), nn.ReLU(), nn.Linear(8, 4)), (3, 2, 2)),
+        "MLP with a softmax tail": (nn.Sequential(nn.Linear(7, 8), nn.ReLU(), nn.Linear(8, 4), nn.Softmax(dim=1)), (7,)),
+        "Linear without bias, Dropout(0)": (nn.Sequential(nn.Linear(7, 8, bias=False), nn.Dropout(0.0), nn.ReLU(), nn.Linear(8, 4)), (7,)),
+        "convolution output as logits": (nn.Sequential(conv(3, 4, 3, padding=1), nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten()), (3, 8, 8)),
+    }
+    refused = {
+        "max pooling with ceil_mode": (nn.Sequential(conv(3, 6, 3, padding=1), nn.MaxPool2d(2, ceil_mode=True), *_head(6)), (3, 9, 9)),
+        "overlapping average pooling": (nn.Sequential(conv(3, 6, 3, padding=1), nn.AvgPool2d(3, 2, 1), *_head(6)), (3, 9, 9)),
+        "adaptive pooling to 2x2": (nn.Sequential(conv(3, 6, 3, padding=1), nn.AdaptiveAvgPool2d((2, 2)), nn.Flatten(), nn.Linear(24, 4)), (3, 8, 8)),
+        "grouped convolution": (nn.Sequential(conv(4, 8, 3, padding=1, groups=2), *_head(8)), (4, 8, 8)),
+        "dilated convolution": (nn.Sequential(conv(3, 6, 3, padding=2, dilation=2), *_head(6)), (3, 8, 8)),
+        "padding='same' on an even kernel": (nn.Sequential(conv(3, 6, 2, padding="same"), *_head(6)), (3, 8, 8)),
+        "dropout with p > 0": (nn.Sequential(nn.Linear(7, 8), nn.Dropout(0.5), nn.Linear(8, 4)), (7,)),
+        "an activation without a kernel": (nn.Sequential(nn.Linear(7, 8), nn.Tanh(), nn.Linear(8, 4)), (7,)),
+    }
+    return ok, refused
+
+
+@pytest.mark.parametrize("name", sorted(_edge_models()[0]))
+def test_edge_geometries_match_autograd_fp64(name):
+    """Layer geometries at the edges of what the five configs use: each must reproduce nested autograd in fp64."""
+    torch.manual_seed(1)
+    model, shape = _edge_models()[0][name]
+    model.train()
+    loss = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, *shape, generator=g)
+    y = torch.randint(0, 4, (3,), generator=g)
+    tape = tracer.trace(model, loss, shape)
+    m64 = model.double()
+    op = ao.AutogradSpectralOperator(m64, [x.double(), y], loss)
+    v = torch.randn(tape.n_params, generator=g, dtype=torch.float64)
+    v = (v / v.norm()).float().double()
+    jo = JetTapeOracle(tape, ao.flat_params(m64), x, y)
+    assert rel_err(jo.run(0).numpy(), op.gradient().detach().numpy()) < 1e-10
+    assert rel_err(jo.run(1, v).numpy(), op.hv(v).numpy()) < 1e-9
+    assert rel_err(jo.vghv(v, mode="reference").numpy(), op.vghv(v).numpy()) < 1e-8
+
+
+@pytest.mark.parametrize("name", sorted(_edge_models()[1]))
+def test_unsupported_geometries_are_refused_by_name(name):
+    """No silent approximation and no CPU fallback: what has no kernel raises UnsupportedModel at trace time."""
+    model, shape = _edge_models()[1][name]
+    with pytest.raises(tracer.UnsupportedModel):
+        tracer.trace(model.train(), torch.nn.CrossEntropyLoss(), shape)
